@@ -1,0 +1,103 @@
+// device.h — the CUDA device behind the C ABI: stream, stream-ordered memory pool, the
+// Cached-module allocation slots, pinned staging, the NVRTC kernel cache and CUDA-graph
+// capture.  Replaces `CudaDevice` (src/devices/cuda/cuda_device.rs:14-127), `KernelCache`
+// (kernel_cache.rs:10-73), `CudaSource` (source.rs:21-66) and `LazyCudaGraph` (lazy.rs:10-72).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.h"
+#include "kernels.h"
+
+// a compiled chain of expressions: one CUmodule holding the vector and the scalar variant
+struct cb_expr {
+    int32_t dtype = 0;
+    int32_t kind = 0;
+    int32_t n_progs = 0;
+    uint64_t key = 0;
+    CUmodule module = nullptr;
+    CUfunction fn_vec = nullptr;
+    CUfunction fn_scalar = nullptr;
+    int threads = 256;
+    int unroll = 4;       // 16-byte units per thread per tile of the vector kernel
+    size_t cubin_bytes = 0;
+};
+
+struct cb_graph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    size_t kernel_nodes = 0;
+};
+
+namespace cb {
+
+// launch-shape tunables (environment, read once): CB_THREADS, CB_UNROLL, CB_MIN_BLOCKS,
+// CB_BLOCKS_PER_SM, CB_LD_MOD, CB_ST_MOD.  Defaults were chosen from the ncu captures under profiles/.
+struct Tunables {
+    int threads = 256;
+    int unroll = 4;
+    int min_blocks = 4;
+    int blocks_per_sm = 8;
+    std::string ld_mod = ".cs";
+    std::string st_mod = ".cs";
+    std::string dump_dir;  // CB_DUMP_DIR: write generated sources and cubins here
+};
+const Tunables &tunables();
+
+// Driver entry points, resolved through cudaGetDriverEntryPoint so the library carries no
+// link-time dependency on libcuda (it must load on a machine without a driver).
+struct DriverApi {
+    CUresult (*ModuleLoadData)(CUmodule *, const void *) = nullptr;
+    CUresult (*ModuleUnload)(CUmodule) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction *, CUmodule, const char *) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                             CUstream, void **, void **) = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char **) = nullptr;
+    bool loaded = false;
+};
+
+// NVRTC: full translation unit for (dtype, kind, programs) and its compilation to an sm_100a cubin
+std::string build_kernel_source(int32_t dtype, int32_t kind, const cb_node *const *progs, const int32_t *n_nodes,
+                                int32_t n_progs, const Tunables &t);
+int32_t compile_cubin(const std::string &source, std::string *cubin, std::string *log);
+
+}  // namespace cb
+
+struct cb_device {
+    int ordinal = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;       // compute stream (the reference's `stream`)
+    cudaStream_t copy_stream = nullptr;  // transfer stream (the reference's `mem_transfer_stream`)
+    cudaMemPool_t pool = nullptr;
+    cb::DriverApi drv;
+    uint64_t launches = 0;
+    bool capturing = false;
+
+    std::unordered_map<uint64_t, std::unique_ptr<cb_expr>> exprs;  // kernel cache keyed by IR hash
+
+    struct Slot {
+        uint64_t ptr;
+        size_t bytes;
+    };
+    std::unordered_map<uint64_t, Slot> cache_slots;  // Cached module: cursor -> allocation
+
+    // pinned staging for pageable host memory
+    void *stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+
+    // reduction scratch
+    void *sum_partials = nullptr;  // kSumMaxBlocks x 8 bytes
+    void *sum_scalar = nullptr;    // 8 bytes device
+    void *sum_host = nullptr;      // 8 bytes pinned
+
+    cb::LaunchCtx ctx() const { return cb::LaunchCtx{stream, sm_count * cb::tunables().blocks_per_sm}; }
+    int32_t cuda_fail(cudaError_t e, const char *what) const;
+    int32_t drv_fail(CUresult r, const char *what) const;
+    int32_t use() const;  // cudaSetDevice
+};

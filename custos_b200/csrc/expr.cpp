@@ -1,0 +1,328 @@
+// expr.cpp — host side of the two_way_ops expression IR.
+//
+// Reference behaviour mirrored here:
+//  * the Combiner tree and its `to_cl_source()` strings (src/two_way_ops/ops.rs,
+//    ops/unary.rs, ops/cmps.rs) — expr_to_cl_source reproduces them byte for byte,
+//    including Rust's `{:?}` rendering of literals (to_cl_source.rs:7-12);
+//  * deliberately NOT mirrored: the CUDA we compile uses typed
+//    literal bit patterns (no double promotion), ternary min/max, `<=` for Eq — i.e. the
+//    semantics of the CPU `Eval` impls, which are the parity target.
+#include "expr.h"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+namespace cb {
+
+bool op_is_binary(int32_t op)
+{
+    return (op >= CB_OP_ADD && op <= CB_OP_MAX) || (op >= CB_OP_GEQ && op <= CB_OP_EQ);
+}
+bool op_is_unary(int32_t op) { return op >= CB_OP_SIN && op <= CB_OP_IDENTITY; }
+
+static const char *op_name(int32_t op)
+{
+    static const char *names[CB_OP_COUNT] = {"x",   "y",   "const", "add", "mul",  "sub", "div", "pow",
+                                             "min", "max", "sin",   "cos", "tan",  "tanh", "exp", "ln",
+                                             "abs", "neg", "identity", "geq", "leq", "eq"};
+    return (op >= 0 && op < CB_OP_COUNT) ? names[op] : "?";
+}
+
+// Which ops exist for which T in the reference: Add/Mul/Sub/Div need core::ops (all
+// numbers); Neg needs core::ops::Neg (floats, signed ints); GEq/LEq/Eq need Number; every
+// other op is bounded by `T: Float` (ops.rs:233,271,309; ops/unary.rs).
+static bool op_supported(int32_t dtype, int32_t op)
+{
+    if (is_float_dtype(dtype)) return true;
+    switch (op) {
+    case CB_OP_X: case CB_OP_Y: case CB_OP_CONST: case CB_OP_ADD: case CB_OP_MUL: case CB_OP_SUB:
+    case CB_OP_DIV: case CB_OP_GEQ: case CB_OP_LEQ: case CB_OP_EQ:
+        return true;
+    case CB_OP_NEG: return is_signed_int_dtype(dtype);
+    default: return false;
+    }
+}
+
+int32_t expr_validate(int32_t dtype, int32_t kind, const cb_node *nodes, int32_t n)
+{
+    if (!valid_dtype(dtype)) return fail(CB_ERR_INVALID_ARG, "invalid dtype %d", dtype);
+    if (!nodes || n <= 0) return fail(CB_ERR_EXPR, "empty expression");
+    if (n > kMaxNodes) return fail(CB_ERR_EXPR, "expression has %d nodes (max %d)", n, kMaxNodes);
+    for (int32_t i = 0; i < n; i++) {
+        const cb_node &c = nodes[i];
+        if (c.op < 0 || c.op >= CB_OP_COUNT) return fail(CB_ERR_EXPR, "node %d: unknown opcode %d", i, c.op);
+        if (!op_supported(dtype, c.op))
+            return fail(CB_ERR_UNSUPPORTED, "node %d: op '%s' is not implemented for dtype %s in the reference",
+                        i, op_name(c.op), dtype_name(dtype));
+        if (c.op == CB_OP_Y && kind >= 0 && kind != CB_KERNEL_BINARY)
+            return fail(CB_ERR_EXPR, "node %d: second marker in a unary expression", i);
+        if (op_is_binary(c.op) || op_is_unary(c.op)) {
+            if (c.a < 0 || c.a >= i) return fail(CB_ERR_EXPR, "node %d: operand a=%d out of order", i, c.a);
+            if (op_is_binary(c.op) && (c.b < 0 || c.b >= i))
+                return fail(CB_ERR_EXPR, "node %d: operand b=%d out of order", i, c.b);
+        }
+        if (c.op == CB_OP_CONST && dtype == CB_F16) {
+            const float f = (float)c.fimm;
+            if (std::isfinite(c.fimm) && (double)host_f16_to_f32(host_f32_to_f16(f)) != c.fimm)
+                return fail(CB_ERR_EXPR, "node %d: literal %.17g is not representable in f16 (round it first)", i,
+                            c.fimm);
+        }
+        if (c.op == CB_OP_CONST && dtype == CB_F32 && std::isfinite(c.fimm) && (double)(float)c.fimm != c.fimm)
+            return fail(CB_ERR_EXPR, "node %d: literal %.17g is not representable in f32 (round it first)", i, c.fimm);
+    }
+    return CB_OK;
+}
+
+int32_t chain_validate(int32_t dtype, int32_t kind, const cb_node *const *progs, const int32_t *n_nodes,
+                       int32_t n_progs)
+{
+    if (kind < CB_KERNEL_APPLY || kind > CB_KERNEL_BINARY) return fail(CB_ERR_INVALID_ARG, "invalid kernel kind %d", kind);
+    if (!progs || !n_nodes || n_progs <= 0) return fail(CB_ERR_EXPR, "no programs");
+    if (kind != CB_KERNEL_APPLY && n_progs != 1)
+        return fail(CB_ERR_EXPR, "only apply kernels take a chain of programs");
+    if (n_progs > 64) return fail(CB_ERR_EXPR, "chain of %d programs (max 64)", n_progs);
+    for (int32_t k = 0; k < n_progs; k++) CB_TRY(expr_validate(dtype, kind, progs[k], n_nodes[k]));
+    return CB_OK;
+}
+
+// ------------------------------------------------------------------ binary16 (host)
+uint16_t host_f32_to_f16(float v)
+{
+    uint32_t u;
+    std::memcpy(&u, &v, 4);
+    const uint32_t sign = (u >> 16) & 0x8000u;
+    u &= 0x7fffffffu;
+    if (u >= 0x7f800000u) return (uint16_t)(sign | 0x7c00u | (u > 0x7f800000u ? 0x0200u | ((u >> 13) & 0x3ffu) : 0u));
+    if (u >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);  // rounds to >= 65520 -> inf
+    if (u < 0x33000001u) return (uint16_t)sign;                // <= 2^-25 -> zero (tie goes to even = 0)
+    // scale so that the 11-bit result sits in an integer, then round to nearest even
+    const int e = (int)(u >> 23);
+    uint32_t sig = (u & 0x7fffffu) | 0x800000u;
+    int shift = (e >= 113) ? 13 : (126 - e);  // normal halfs drop 13 bits, subnormals more
+    const uint32_t q = sig >> shift;
+    const uint32_t rem = sig & ((1u << shift) - 1u);
+    const uint32_t half = 1u << (shift - 1);
+    uint32_t r = q + ((rem > half || (rem == half && (q & 1u))) ? 1u : 0u);
+    if (e >= 113) r += (uint32_t)(e - 113) << 10;  // r holds the implicit bit at 0x400: exponent field e-112
+    return (uint16_t)(sign | r);
+}
+
+float host_f16_to_f32(uint16_t h)
+{
+    const int s = (h >> 15) & 1, e = (h >> 10) & 0x1f, m = h & 0x3ff;
+    float r;
+    if (e == 0) r = std::ldexp((float)m, -24);
+    else if (e == 31) r = m ? NAN : INFINITY;
+    else r = std::ldexp((float)(m | 0x400), e - 25);
+    return s ? -r : r;
+}
+
+// ------------------------------------------------------------ Rust `{:?}` for numbers
+// core::fmt::float: shortest digits that round-trip; decimal with at least one
+// fractional digit when 1e-4 <= |v| < 1e16 (or v == 0), exponential ("1e16", "1.5e-7")
+// otherwise; "NaN", "inf", "-inf".
+static std::string rust_debug_float(double v, bool single)
+{
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v < 0 ? "-inf" : "inf";
+    std::string out;
+    if (std::signbit(v)) out += "-";
+    const double a = std::fabs(v);
+    if (a == 0.0) return out + "0.0";
+
+    char buf[64];
+    int prec = 1;
+    for (; prec <= 17; prec++) {
+        std::snprintf(buf, sizeof buf, "%.*e", prec - 1, a);
+        if (single ? (std::strtof(buf, nullptr) == (float)a) : (std::strtod(buf, nullptr) == a)) break;
+    }
+    // buf = d.ddddde[+-]XX
+    std::string digits;
+    const char *p = buf;
+    for (; *p && *p != 'e'; p++)
+        if (*p != '.') digits += *p;
+    const int exp10 = std::atoi(p + 1);
+    while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+    const int nd = (int)digits.size();
+
+    if (a >= 1e-4 && a < 1e16) {
+        if (exp10 >= nd - 1) {
+            out += digits + std::string((size_t)(exp10 - (nd - 1)), '0') + ".0";
+        } else if (exp10 >= 0) {
+            out += digits.substr(0, (size_t)exp10 + 1) + "." + digits.substr((size_t)exp10 + 1);
+        } else {
+            out += "0." + std::string((size_t)(-exp10 - 1), '0') + digits;
+        }
+    } else {
+        out += digits.substr(0, 1);
+        if (nd > 1) out += "." + digits.substr(1);
+        out += "e" + std::to_string(exp10);
+    }
+    return out;
+}
+
+std::string rust_debug_literal(int32_t dtype, const cb_node &c)
+{
+    switch (dtype) {
+    case CB_F32: return rust_debug_float((double)(float)c.fimm, true);
+    case CB_F64: return rust_debug_float(c.fimm, false);
+    case CB_F16: return rust_debug_float((double)host_f16_to_f32(host_f32_to_f16((float)c.fimm)), true);  // half: Debug via f32
+    case CB_U32: return std::to_string((uint32_t)c.iimm);
+    case CB_U8: return std::to_string((unsigned)(uint8_t)c.iimm);
+    case CB_I32: return std::to_string((int32_t)c.iimm);
+    default: return std::to_string((long long)c.iimm);
+    }
+}
+
+std::string expr_to_cl_source(int32_t dtype, const cb_node *nodes, int32_t n, const char *marker_x,
+                              const char *marker_y)
+{
+    std::vector<std::string> s((size_t)n);
+    for (int32_t i = 0; i < n; i++) {
+        const cb_node &c = nodes[i];
+        const std::string a = c.a >= 0 ? s[(size_t)c.a] : std::string();
+        const std::string b = c.b >= 0 ? s[(size_t)c.b] : std::string();
+        switch (c.op) {
+        case CB_OP_X: s[i] = marker_x ? marker_x : "x"; break;
+        case CB_OP_Y: s[i] = marker_y ? marker_y : "y"; break;
+        case CB_OP_CONST: s[i] = rust_debug_literal(dtype, c); break;
+        case CB_OP_ADD: s[i] = "(" + a + " + " + b + ")"; break;
+        case CB_OP_MUL: s[i] = "(" + a + " * " + b + ")"; break;
+        case CB_OP_SUB: s[i] = "(" + a + " - " + b + ")"; break;
+        case CB_OP_DIV: s[i] = "(" + a + " / " + b + ")"; break;
+        case CB_OP_POW: s[i] = "pow(" + a + ", " + b + ")"; break;
+        case CB_OP_MIN: s[i] = "min(" + a + ", " + b + ")"; break;
+        case CB_OP_MAX: s[i] = "max(" + a + ", " + b + ")"; break;
+        case CB_OP_SIN: s[i] = "sin(" + a + ")"; break;
+        case CB_OP_COS: s[i] = "cos(" + a + ")"; break;
+        case CB_OP_TAN: s[i] = "tan(" + a + ")"; break;
+        case CB_OP_TANH: s[i] = "tanh(" + a + ")"; break;
+        case CB_OP_EXP: s[i] = "exp(" + a + ")"; break;
+        case CB_OP_LN: s[i] = "log(" + a + ")"; break;
+        case CB_OP_ABS: s[i] = "abs(" + a + ")"; break;
+        case CB_OP_NEG: s[i] = "-(" + a + ")"; break;
+        case CB_OP_IDENTITY: s[i] = a; break;
+        case CB_OP_GEQ: s[i] = "(" + a + " >= " + b + ")"; break;
+        case CB_OP_LEQ: s[i] = "(" + a + " <= " + b + ")"; break;
+        case CB_OP_EQ: s[i] = "(" + a + " == " + b + ")"; break;
+        default: break;
+        }
+    }
+    return s[(size_t)n - 1];
+}
+
+// ------------------------------------------------------------------ CUDA codegen
+// A literal is emitted as its exact bit pattern in the compute dtype, so `x * 2.0`
+// is an f32 multiply by 2.0f (the reference CUDA path would promote to double).
+static std::string cuda_literal(int32_t dtype, const cb_node &c)
+{
+    char buf[96];
+    switch (dtype) {
+    case CB_F32: {
+        const float f = (float)c.fimm;
+        uint32_t u;
+        std::memcpy(&u, &f, 4);
+        std::snprintf(buf, sizeof buf, "__uint_as_float(0x%08xu)", u);
+    } break;
+    case CB_F64: {
+        uint64_t u;
+        std::memcpy(&u, &c.fimm, 8);
+        std::snprintf(buf, sizeof buf, "__longlong_as_double((long long)0x%016llxULL)", (unsigned long long)u);
+    } break;
+    case CB_F16: std::snprintf(buf, sizeof buf, "((T)0x%04xu)", (unsigned)host_f32_to_f16((float)c.fimm)); break;
+    case CB_I32: std::snprintf(buf, sizeof buf, "((T)0x%08xu)", (unsigned)(uint32_t)(int32_t)c.iimm); break;
+    case CB_U32: std::snprintf(buf, sizeof buf, "((T)0x%08xu)", (unsigned)(uint32_t)c.iimm); break;
+    case CB_U8: std::snprintf(buf, sizeof buf, "((T)0x%02xu)", (unsigned)(uint8_t)c.iimm); break;
+    default: std::snprintf(buf, sizeof buf, "((T)0x%016llxULL)", (unsigned long long)c.iimm); break;
+    }
+    return buf;
+}
+
+static const char *cuda_fn(int32_t op)
+{
+    switch (op) {
+    case CB_OP_ADD: return "cb_add";
+    case CB_OP_MUL: return "cb_mul";
+    case CB_OP_SUB: return "cb_sub";
+    case CB_OP_DIV: return "cb_div";
+    case CB_OP_POW: return "cb_pow";
+    case CB_OP_MIN: return "cb_min";
+    case CB_OP_MAX: return "cb_max";
+    case CB_OP_SIN: return "cb_sin";
+    case CB_OP_COS: return "cb_cos";
+    case CB_OP_TAN: return "cb_tan";
+    case CB_OP_TANH: return "cb_tanh";
+    case CB_OP_EXP: return "cb_exp";
+    case CB_OP_LN: return "cb_ln";
+    case CB_OP_ABS: return "cb_abs";
+    case CB_OP_NEG: return "cb_neg";
+    case CB_OP_IDENTITY: return "cb_identity";
+    case CB_OP_GEQ: return "cb_geq";
+    case CB_OP_LEQ: return "cb_leq";
+    case CB_OP_EQ: return "cb_eq";
+    default: return "cb_bad";
+    }
+}
+
+std::string expr_cuda_function(int32_t dtype, const cb_node *const *progs, const int32_t *n_nodes,
+                               int32_t n_progs)
+{
+    std::string s;
+    s += "// generated from the recorded Combiner trees; one block per recorded op, applied in order\n";
+    s += "namespace CB_NS {\n__device__ __forceinline__ T cb_fn(T x, T y)\n{\n";
+    for (int32_t k = 0; k < n_progs; k++) {
+        const cb_node *nd = progs[k];
+        const int32_t n = n_nodes[k];
+        s += "    { // op " + std::to_string(k) + ": x = " + expr_to_cl_source(dtype, nd, n, "x", "y") + "\n";
+        for (int32_t i = 0; i < n; i++) {
+            const cb_node &c = nd[i];
+            const std::string name = "t" + std::to_string(i);
+            std::string rhs;
+            if (c.op == CB_OP_X) rhs = "x";
+            else if (c.op == CB_OP_Y) rhs = "y";
+            else if (c.op == CB_OP_CONST) rhs = cuda_literal(dtype, c) + " /* " + rust_debug_literal(dtype, c) + " */";
+            else if (op_is_binary(c.op))
+                rhs = std::string(cuda_fn(c.op)) + "(t" + std::to_string(c.a) + ", t" + std::to_string(c.b) + ")";
+            else
+                rhs = std::string(cuda_fn(c.op)) + "(t" + std::to_string(c.a) + ")";
+            s += "        const T " + name + " = " + rhs + ";\n";
+        }
+        s += "        x = t" + std::to_string(n - 1) + ";\n    }\n";
+    }
+    s += "    return x;\n}\n}  // namespace CB_NS\n";
+    return s;
+}
+
+uint64_t chain_hash(int32_t dtype, int32_t kind, const cb_node *const *progs, const int32_t *n_nodes,
+                    int32_t n_progs)
+{
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&h](uint64_t v) {
+        for (int i = 0; i < 8; i++) {
+            h ^= (v >> (8 * i)) & 0xffu;
+            h *= 1099511628211ull;
+        }
+    };
+    mix((uint64_t)dtype);
+    mix((uint64_t)kind);
+    mix((uint64_t)n_progs);
+    for (int32_t k = 0; k < n_progs; k++) {
+        mix((uint64_t)n_nodes[k]);
+        for (int32_t i = 0; i < n_nodes[k]; i++) {
+            const cb_node &c = progs[k][i];
+            mix((uint64_t)(uint32_t)c.op);
+            mix((uint64_t)(uint32_t)c.a);
+            mix((uint64_t)(uint32_t)c.b);
+            if (c.op == CB_OP_CONST) {
+                uint64_t bits;
+                if (is_float_dtype(dtype)) std::memcpy(&bits, &c.fimm, 8);
+                else bits = (uint64_t)c.iimm;
+                mix(bits);
+            }
+        }
+    }
+    return h;
+}
+
+}  // namespace cb

@@ -1,0 +1,42 @@
+// expr.h — the two_way_ops expression IR on the host: validation, the reference's
+// `to_cl_source()` rendering, and the typed CUDA source this backend compiles.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "common.h"
+
+namespace cb {
+
+constexpr int kMaxNodes = 256;
+
+// true for ops taking two operands
+bool op_is_binary(int32_t op);
+bool op_is_unary(int32_t op);
+
+// Checks the node array (topological order, operand indices, ops legal for the dtype,
+// markers legal for the kernel kind).  kind < 0 = no kernel-kind restriction.
+int32_t expr_validate(int32_t dtype, int32_t kind, const cb_node *nodes, int32_t n);
+int32_t chain_validate(int32_t dtype, int32_t kind, const cb_node *const *progs, const int32_t *n_nodes,
+                       int32_t n_progs);
+
+// Rust `{:?}` of a literal of the dtype (src/two_way_ops/to_cl_source.rs:7-12)
+std::string rust_debug_literal(int32_t dtype, const cb_node &c);
+
+// `to_cl_source()` of the tree, the reference's format strings
+std::string expr_to_cl_source(int32_t dtype, const cb_node *nodes, int32_t n, const char *marker_x,
+                              const char *marker_y);
+
+// The generated part of the translation unit: `cb_fn(x, y)` applying the programs in order.
+std::string expr_cuda_function(int32_t dtype, const cb_node *const *progs, const int32_t *n_nodes,
+                               int32_t n_progs);
+
+// 64-bit key of (dtype, kind, programs) for the kernel cache
+uint64_t chain_hash(int32_t dtype, int32_t kind, const cb_node *const *progs, const int32_t *n_nodes,
+                    int32_t n_progs);
+
+// IEEE binary16 <-> binary32, round to nearest even (host side, for f16 literals)
+uint16_t host_f32_to_f16(float v);
+float host_f16_to_f32(uint16_t h);
+
+}  // namespace cb

@@ -1,0 +1,30 @@
+// kernels.h — host launchers of the ahead-of-time compiled kernels in kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "../../include/custos_b200.h"
+
+namespace cb {
+
+struct LaunchCtx {
+    cudaStream_t stream;
+    int max_blocks;  // persistent-grid cap: SM count x resident blocks per SM
+};
+
+// fixed, hardware-independent upper bound on pass-1 blocks of the sum (8 per SM on a 148-SM B200)
+constexpr int kSumMaxBlocks = 1184;
+
+cudaError_t launch_binary(const LaunchCtx &ctx, int dtype, int op, const void *lhs, const void *rhs, void *out, size_t n);
+cudaError_t launch_fill(const LaunchCtx &ctx, void *out, size_t n, int elem_bytes, uint64_t pattern);
+int launch_fill_count(const void *out, size_t n, int elem_bytes);
+cudaError_t launch_copy(const LaunchCtx &ctx, void *dst, const void *src, size_t bytes);
+int launch_copy_count(const void *dst, const void *src, size_t bytes);
+void sum_plan(int dtype, size_t n, int *blocks, size_t *chunk, int *threads, int *vec, int *threads2);
+// partials: device scratch of kSumMaxBlocks accumulators; out: device scalar of the accumulation type
+cudaError_t launch_sum(const LaunchCtx &ctx, int dtype, const void *in, size_t n, void *partials, void *out, size_t divisor);
+cudaError_t launch_fold_ranks(const LaunchCtx &ctx, int dtype, const void *gathered, int n_ranks, void *out, size_t divisor);
+
+}  // namespace cb

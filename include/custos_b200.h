@@ -1,0 +1,382 @@
+/*
+ * custos_b200.h — the C ABI of the Blackwell-native custos backend.
+ *
+ * This is the drop-in boundary for the data-parallel hot path of
+ * elftausend/custos (element-wise unary/binary ops, fused unary chains,
+ * unary gradients, clear/copy, sum/mean).  A Rust `CUDA<Mods>` device would
+ * bind exactly these entry points in place of the driver/NVRTC FFI it calls
+ * today (reference: src/devices/cuda/api/ffi.rs:165-263 and
+ * src/devices/cuda/api/nvrtc/ffi.rs:36-54).  INTEGRATION.md shows the
+ * `extern "C"` block a maintainer would add.
+ *
+ * Conventions
+ *  - every function returns an int32 status: 0 = CB_OK, otherwise a cb_status
+ *    (values >= 1000 are `1000 + cudaError_t`, >= 2000 are `2000 + ncclResult_t`,
+ *    >= 3000 are `3000 + nvrtcResult`); the text is available through
+ *    cb_last_error() (thread local).  This mirrors `type Error = i32` of the
+ *    reference device (src/devices/cuda/cuda.rs:70-73).
+ *  - device memory is passed as raw 64-bit device addresses, exactly like
+ *    `CUDAPtr.ptr` (src/devices/cuda/cuda_ptr.rs:7-15).
+ *  - lengths are element counts (size_t, 64-bit indexing inside the kernels);
+ *    the reference passes `usize` but its kernels declare `int`
+ *    (src/devices/cuda/ops.rs:155,174).
+ *  - a device handle is single-threaded, like the reference's RefCell-based
+ *    device (src/devices/cuda/cuda_device.rs:14-29).
+ *  - there is no CPU fallback anywhere behind this header: if no CUDA device
+ *    is usable every compute entry point returns an error.
+ */
+#ifndef CUSTOS_B200_H
+#define CUSTOS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB_ABI_VERSION 1
+
+/* ------------------------------------------------------------------ status */
+typedef enum cb_status {
+    CB_OK = 0,
+    CB_ERR_INVALID_ARG = 1,
+    CB_ERR_ZERO_LENGTH = 2,     /* DeviceError::ZeroLengthBuffer / CudaErrorKind::InvalidAllocSize
+                                   (src/devices/cuda/api/cuda.rs:69-71, src/devices/cpu/cpu_device.rs:135-137) */
+    CB_ERR_NO_DEVICE = 3,       /* no usable CUDA device: never falls back to the CPU */
+    CB_ERR_UNSUPPORTED = 4,
+    CB_ERR_EXPR = 5,            /* malformed expression IR */
+    CB_ERR_INVALID_LAZY_BUF = 6,/* DeviceError::InvalidLazyBuf (src/error.rs:29-56) */
+    CB_ERR_MISSING_CACHE_TRACES = 7, /* DeviceError::MissingCacheTraces */
+    CB_ERR_GRAPH_OPTIMIZATION = 8,   /* DeviceError::GraphOptimization */
+    CB_ERR_SHAPE = 9,
+    CB_ERR_STATE = 10,
+    CB_ERR_CUDA = 1000,
+    CB_ERR_NCCL = 2000,
+    CB_ERR_NVRTC = 3000
+} cb_status;
+
+const char *cb_last_error(void);
+int32_t cb_abi_version(void);
+
+/* ------------------------------------------------------------------ dtypes */
+/* CDatatype (src/devices/cdatatype.rs:3-62).  bf16 is deliberately absent: the
+ * reference maps it to "half", which is wrong (cdatatype.rs:58-62). */
+typedef enum cb_dtype {
+    CB_F32 = 0,
+    CB_F64 = 1,
+    CB_F16 = 2,   /* IEEE binary16 storage; arithmetic in f32 with a round-to-nearest-even
+                     after EVERY op, like `half` on the reference CPU device
+                     (src/number.rs:543-608) */
+    CB_I32 = 3,
+    CB_I64 = 4,
+    CB_U32 = 5,
+    CB_U8  = 6,
+    CB_DTYPE_COUNT = 7
+} cb_dtype;
+
+size_t cb_dtype_size(int32_t dtype);
+
+/* ------------------------------------------------- expression IR (two_way_ops) */
+/* One node of a `Combiner` tree (src/two_way_ops/combiner.rs:8-116).  A program
+ * is an array of nodes in topological order (operands before users); the last
+ * node is the value of the expression.  `a`/`b` index earlier nodes. */
+typedef enum cb_opcode {
+    CB_OP_X = 0,        /* first marker / seed value: Resolve (resolve.rs:25-30)            */
+    CB_OP_Y = 1,        /* second marker (two-argument closures, mod.rs:96-104)             */
+    CB_OP_CONST = 2,    /* numeric literal operand                                          */
+    CB_OP_ADD = 3,      /* ops.rs:53-103   "(a + b)"                                        */
+    CB_OP_MUL = 4,      /* ops.rs:14-58    "(a * b)"                                        */
+    CB_OP_SUB = 5,      /* ops.rs:105-148  "(a - b)"                                        */
+    CB_OP_DIV = 6,      /* ops.rs:150-193  "(a / b)"                                        */
+    CB_OP_POW = 7,      /* ops.rs:195-238  "pow(a, b)"                                      */
+    CB_OP_MIN = 8,      /* ops.rs:240-276  "min(a, b)"  eval: if a < b {a} else {b}         */
+    CB_OP_MAX = 9,      /* ops.rs:278-314  "max(a, b)"  eval: if a > b {a} else {b}         */
+    CB_OP_SIN = 10,     /* ops/unary.rs                                                     */
+    CB_OP_COS = 11,
+    CB_OP_TAN = 12,     /* f16: evaluates cos() on the reference CPU (number.rs:575-577)    */
+    CB_OP_TANH = 13,
+    CB_OP_EXP = 14,
+    CB_OP_LN = 15,      /* "log(a)"                                                         */
+    CB_OP_ABS = 16,
+    CB_OP_NEG = 17,     /* "-(a)"                                                           */
+    CB_OP_IDENTITY = 18,
+    CB_OP_GEQ = 19,     /* ops/cmps.rs:42-47   "(a >= b)" -> 0/1 in T                       */
+    CB_OP_LEQ = 20,     /* ops/cmps.rs:87-92   "(a <= b)"                                   */
+    CB_OP_EQ = 21,      /* ops/cmps.rs:132-137 source "(a == b)", but eval is a <= b (:135);
+                           this backend follows the CPU eval                                */
+    CB_OP_COUNT = 22
+} cb_opcode;
+
+typedef struct cb_node {
+    int32_t op;   /* cb_opcode */
+    int32_t a;    /* operand node index, -1 if unused */
+    int32_t b;    /* operand node index, -1 if unused */
+    int32_t _pad;
+    double  fimm; /* CB_OP_CONST for float dtypes (exact for f16/f32/f64 literals) */
+    int64_t iimm; /* CB_OP_CONST for integer dtypes */
+} cb_node;
+
+/* `to_cl_source()` of the tree, byte-for-byte in the reference's format
+ * (src/two_way_ops/to_cl_source.rs:7-12 + the per-op format strings); markers
+ * are given by the caller ("x", "x[idx]", "lhs[idx]" ...).  Writes a
+ * NUL-terminated string, returns CB_ERR_INVALID_ARG if cap is too small. */
+int32_t cb_expr_to_cl_source(int32_t dtype, const cb_node *nodes, int32_t n_nodes,
+                             const char *marker_x, const char *marker_y,
+                             char *out, size_t cap);
+
+/* `operations_to_fused_src` (src/devices/fusing.rs:4-19): "x = <src>;\n" per op. */
+int32_t cb_ops_to_fused_src(int32_t dtype, const cb_node *const *progs, const int32_t *n_nodes,
+                            int32_t n_progs, char *out, size_t cap);
+
+/* The sm_100a CUDA source this backend generates for a chain of programs
+ * (typed literals, no double promotion, no FMA contraction).  kind: see cb_kernel_kind. */
+typedef enum cb_kernel_kind {
+    CB_KERNEL_APPLY = 0,       /* out[i] = fN(...f1(in[i]))              K1/K2, a1/a8 */
+    CB_KERNEL_UNARY_GRAD = 1,  /* lhs_grad[i] += out_grad[i] * g(lhs[i]) K3, a2       */
+    CB_KERNEL_BINARY = 2       /* out[i] = f(lhs[i], rhs[i])             a5 (+ f2)    */
+} cb_kernel_kind;
+
+int32_t cb_expr_cuda_source(int32_t dtype, int32_t kind, const cb_node *const *progs,
+                            const int32_t *n_nodes, int32_t n_progs, char *out, size_t cap);
+
+/* Compile (NVRTC, --gpu-architecture=sm_100a --fmad=false, no fast-math) without a
+ * device: returns the cubin size.  Used by the build check and the CPU-side tests. */
+int32_t cb_expr_compile_check(int32_t dtype, int32_t kind, const cb_node *const *progs,
+                              const int32_t *n_nodes, int32_t n_progs, size_t *cubin_bytes);
+
+/* ------------------------------------------------------------------ device */
+typedef struct cb_device cb_device;
+typedef struct cb_expr cb_expr;     /* a compiled (chain of) expression(s) */
+typedef struct cb_graph cb_graph;   /* an instantiated CUDA graph */
+
+/* CUDA::new(idx) (src/devices/cuda/cuda.rs:53-67).  ordinal < 0 = honour
+ * CUSTOS_CU_DEVICE_IDX (src/devices/cuda/mod.rs:35-42), default 0. */
+int32_t cb_device_create(int32_t ordinal, cb_device **out);
+int32_t cb_device_destroy(cb_device *dev);
+int32_t cb_device_ordinal(cb_device *dev, int32_t *ordinal);
+int32_t cb_device_sm_count(cb_device *dev, int32_t *sms);
+/* raw cudaStream_t of the compute stream (for event timing by the harness) */
+int32_t cb_device_stream(cb_device *dev, void **stream);
+int32_t cb_sync(cb_device *dev);
+
+/* Alloc::alloc (src/devices/cuda/cuda.rs:114-123, cuda_ptr.rs:21-30).  zero != 0
+ * gives the zero-initialised memory the CPU device hands out
+ * (src/devices/cpu/cpu_ptr.rs:76-89); gradient buffers rely on it.
+ * bytes == 0 -> CB_ERR_ZERO_LENGTH.  Memory comes from a stream-ordered pool
+ * and is 256-byte aligned. */
+int32_t cb_alloc(cb_device *dev, size_t bytes, int32_t zero, uint64_t *dptr);
+int32_t cb_free(cb_device *dev, uint64_t dptr);          /* CUDAPtr::drop (cuda_ptr.rs:64-77) */
+int32_t cb_mem_info(cb_device *dev, size_t *pool_reserved, size_t *pool_used);
+
+/* Cached module slot (src/modules/cached.rs:173-229): the k-th retrieve of a loop
+ * iteration returns the k-th allocation.  *hit is 1 when the slot existed. */
+int32_t cb_cache_retrieve(cb_device *dev, uint64_t cursor, size_t bytes, uint64_t *dptr, int32_t *hit);
+int32_t cb_cache_clear(cb_device *dev);
+
+/* Read / WriteBuf::write / alloc_from_slice (src/devices/cuda/ops.rs:17-49,101-105,
+ * cuda.rs:124-137).  Host pointers may be pageable; transfers are staged through
+ * pinned buffers owned by the device.  cb_d2h synchronises. */
+int32_t cb_h2d(cb_device *dev, uint64_t dst, const void *src, size_t bytes);
+int32_t cb_d2h(cb_device *dev, void *dst, uint64_t src, size_t bytes);
+/* pinned host memory for zero-copy-staging callers */
+int32_t cb_host_alloc(size_t bytes, void **out);
+int32_t cb_host_free(void *p);
+/* asynchronous variants on the compute stream; host memory must be pinned */
+int32_t cb_h2d_async(cb_device *dev, uint64_t dst, const void *src, size_t bytes);
+int32_t cb_d2h_async(cb_device *dev, void *dst, uint64_t src, size_t bytes);
+
+/* CopySlice::copy_slice_to / WriteBuf::write_buf / CloneBuf (src/devices/cuda/ops.rs:65-116,
+ * cuda.rs:152-164): device to device copy of n elements with element offsets. */
+int32_t cb_copy(cb_device *dev, int32_t dtype, uint64_t dst, size_t dst_off,
+                uint64_t src, size_t src_off, size_t n);
+/* ClearBuf::clear / ZeroGrad::zero_grad (src/devices/cuda/mod.rs:59-74) */
+int32_t cb_clear(cb_device *dev, int32_t dtype, uint64_t dptr, size_t n);
+/* device-side seed for backward(): replaces `vec![T::one(); len]` + write
+ * (src/buffer/impl_autograd.rs:32, src/modules/autograd/tape.rs:53-64) */
+int32_t cb_fill(cb_device *dev, int32_t dtype, uint64_t dptr, size_t n, double fvalue, int64_t ivalue);
+
+/* ------------------------------------------------- compiled expression kernels */
+/* Compile one expression (n_progs = 1, unfused apply_fn: K1) or a chain of unary
+ * expressions applied in order (fused chain: K2, src/devices/cuda/fusing.rs:20-50)
+ * into ONE sm_100a kernel.  Cached by (dtype, kind, IR hash) per device. */
+int32_t cb_expr_compile(cb_device *dev, int32_t dtype, int32_t kind,
+                        const cb_node *const *progs, const int32_t *n_nodes, int32_t n_progs,
+                        cb_expr **out);
+int32_t cb_expr_release(cb_expr *e);   /* expressions are owned by the device cache; no-op kept for symmetry */
+
+/* ApplyFunction::apply_fn body (src/devices/cuda/ops.rs:144-177) and the fused
+ * chain body (src/devices/cuda/fusing.rs:28-49): out[i] = f(in[i]). */
+int32_t cb_apply(cb_device *dev, cb_expr *f, uint64_t in, uint64_t out, size_t n);
+/* UnaryGrad::add_unary_grad body (src/devices/cuda/ops.rs:196-234):
+ * lhs_grad[i] += out_grad[i] * g(lhs[i]) — multiply then add, two roundings
+ * (src/devices/cpu_stack_ops.rs:28). */
+int32_t cb_unary_grad(cb_device *dev, cb_expr *g, uint64_t lhs, uint64_t lhs_grad,
+                      uint64_t out_grad, size_t n);
+/* two-marker expression: out[i] = f(lhs[i], rhs[i]) */
+int32_t cb_apply2(cb_device *dev, cb_expr *f, uint64_t lhs, uint64_t rhs, uint64_t out, size_t n);
+
+/* Binary element-wise add/mul/sub/div — the `AddEw`/`MulBuf` pattern
+ * (README.md:96-122, tests/demo_impl/cuda/mod.rs:3-36, src/lib.rs:293-301). */
+typedef enum cb_binop { CB_BIN_ADD = 0, CB_BIN_MUL = 1, CB_BIN_SUB = 2, CB_BIN_DIV = 3 } cb_binop;
+int32_t cb_binary(cb_device *dev, int32_t dtype, int32_t op, uint64_t lhs, uint64_t rhs,
+                  uint64_t out, size_t n);
+
+/* ------------------------------------------------------------- reductions */
+/* Deterministic two-pass sum (no atomics, fixed grid): pass 1 = per-block tree over
+ * a contiguous chunk, pass 2 = one block folds the partials in index order.
+ * The result is written to a device scalar of the accumulation type
+ * (f32 -> f32, f64 -> f64, f16 -> f32, integers -> i64) at `out`.
+ * The reference has no sum; the order is defined in DESIGN.md. */
+int32_t cb_sum(cb_device *dev, int32_t dtype, uint64_t in, size_t n, uint64_t out);
+int32_t cb_mean(cb_device *dev, int32_t dtype, uint64_t in, size_t n, uint64_t out);
+/* convenience: reduce and copy the scalar to the host (synchronises) */
+int32_t cb_sum_host(cb_device *dev, int32_t dtype, uint64_t in, size_t n, void *host_out);
+int32_t cb_mean_host(cb_device *dev, int32_t dtype, uint64_t in, size_t n, void *host_out);
+/* the fixed (hardware independent) reduction order for n elements: pass 1 runs
+ * `blocks` blocks of `threads` threads over chunks of `chunk` elements reading
+ * `vec` elements per access; pass 2 is one block of `threads2` threads. */
+int32_t cb_sum_plan(int32_t dtype, size_t n, int32_t *blocks, size_t *chunk, int32_t *threads,
+                    int32_t *vec, int32_t *threads2);
+
+/* ------------------------------------------------ CUDA graph capture / replay */
+/* LazyCudaGraph (src/devices/cuda/lazy.rs:10-72): capture the launches issued on
+ * the compute stream between begin/end, instantiate once, replay many times. */
+int32_t cb_graph_begin(cb_device *dev);
+int32_t cb_graph_end(cb_device *dev, cb_graph **out);
+int32_t cb_graph_launch(cb_device *dev, cb_graph *g);
+int32_t cb_graph_destroy(cb_graph *g);
+int32_t cb_graph_node_count(cb_graph *g, size_t *kernel_nodes);
+
+/* CUDA events on the compute stream, for device-side timing by the harness
+ * (torch.cuda.Event only sees torch's own streams) */
+typedef struct cb_event cb_event;
+int32_t cb_event_create(cb_device *dev, cb_event **out);
+int32_t cb_event_record(cb_device *dev, cb_event *ev);
+int32_t cb_event_sync(cb_event *ev);
+int32_t cb_event_elapsed_ms(cb_event *start, cb_event *end, float *ms);
+int32_t cb_event_destroy(cb_event *ev);
+
+/* kernels launched by this library on this device since creation (the harness's
+ * `gpu_launches` evidence) */
+int32_t cb_launch_count(cb_device *dev, uint64_t *count);
+
+/* ------------------------------------------------------ multi-GPU (NCCL) */
+/* One process per GPU.  Element-wise work needs no communication; only the
+ * reduction partials are exchanged: all-gather of one scalar per rank followed
+ * by a rank-ordered fold on every rank (deterministic). */
+typedef struct cb_comm cb_comm;
+#define CB_COMM_ID_BYTES 128
+int32_t cb_comm_unique_id(uint8_t id[CB_COMM_ID_BYTES]);
+int32_t cb_comm_create(cb_device *dev, int32_t n_ranks, int32_t rank,
+                       const uint8_t id[CB_COMM_ID_BYTES], cb_comm **out);
+int32_t cb_comm_destroy(cb_comm *c);
+/* local two-pass sum of `in`, then exchange + rank-ordered fold; out = device scalar */
+int32_t cb_comm_sum(cb_comm *c, int32_t dtype, uint64_t in, size_t n_local, uint64_t out);
+int32_t cb_comm_mean(cb_comm *c, int32_t dtype, uint64_t in, size_t n_local, size_t n_global,
+                     uint64_t out);
+/* contiguous slice [begin, end) of rank r out of n_ranks over n elements, 16-byte aligned starts */
+int32_t cb_shard_range(size_t n, int32_t elem_bytes, int32_t n_ranks, int32_t rank,
+                       size_t *begin, size_t *end);
+
+/* ================================================================ module layer
+ * A C++ restatement of custos' module stack around the device above
+ * (Base, Cached, Lazy, Graph, Autograd: src/modules/*.rs), exported so that the
+ * parity tests can drive `CUDA<Graph<Lazy<Autograd<Base>>>>`-style devices
+ * without a Rust toolchain.  A Rust build would keep its own module layer and
+ * bind only the functions above. */
+typedef struct cbm_device cbm_device;
+typedef uint64_t cbm_buf;   /* buffer handle (not a device address) */
+
+#define CBM_BASE     0u
+#define CBM_CACHED   1u     /* Cached<..>   src/modules/cached.rs   */
+#define CBM_LAZY     2u     /* Lazy<..>     src/modules/lazy.rs     */
+#define CBM_GRAPH    4u     /* Graph<..>    src/modules/graph.rs    */
+#define CBM_AUTOGRAD 8u     /* Autograd<..> src/modules/autograd.rs */
+
+int32_t cbm_device_create(int32_t ordinal, uint32_t modules, int32_t dtype, cbm_device **out);
+int32_t cbm_device_destroy(cbm_device *d);
+int32_t cbm_device_raw(cbm_device *d, cb_device **raw);
+
+/* Buffer::new / device.buffer([..]) (src/buffer.rs:80-93): allocated immediately, zeroed */
+int32_t cbm_buffer_new(cbm_device *d, int32_t dtype, size_t len, cbm_buf *out);
+int32_t cbm_buffer_from_host(cbm_device *d, int32_t dtype, const void *data, size_t len, cbm_buf *out);
+int32_t cbm_buffer_drop(cbm_device *d, cbm_buf b);
+int32_t cbm_buffer_len(cbm_device *d, cbm_buf b, size_t *len);
+/* Buffer::replace().read(): resolves lazily retrieved buffers (src/modules/lazy.rs:430-455) */
+int32_t cbm_buffer_read(cbm_device *d, cbm_buf b, void *host_out, size_t len);
+int32_t cbm_buffer_write(cbm_device *d, cbm_buf b, const void *host_in, size_t len);
+/* device address behind the handle after replace(); 0 when a lazy buffer is not allocated yet */
+int32_t cbm_buffer_ptr(cbm_device *d, cbm_buf b, uint64_t *dptr);
+/* HasId::id(): graph level id (cursor for retrieved buffers, address for eager ones) */
+int32_t cbm_buffer_id(cbm_device *d, cbm_buf b, uint64_t *id);
+int32_t cbm_buffer_require_grad(cbm_device *d, cbm_buf b);   /* Buffer::require_grad */
+int32_t cbm_buffer_requires_grad(cbm_device *d, cbm_buf b, int32_t *flag);
+int32_t cbm_buffer_checkpoint(cbm_device *d, cbm_buf b);     /* Buffer::checkpoint (src/buffer.rs:131-137) */
+
+/* Retriever::retrieve (src/devices.rs:172-186) */
+int32_t cbm_retrieve(cbm_device *d, int32_t dtype, size_t len, const cbm_buf *parents,
+                     int32_t n_parents, cbm_buf *out);
+/* ApplyFunction::apply_fn (src/unary.rs:7-28) */
+int32_t cbm_apply_fn(cbm_device *d, cbm_buf in, const cb_node *nodes, int32_t n_nodes, cbm_buf *out);
+/* UnaryGrad::add_unary_grad (src/unary.rs:31-58) */
+int32_t cbm_add_unary_grad(cbm_device *d, cbm_buf lhs, cbm_buf lhs_grad, cbm_buf out_grad,
+                           const cb_node *nodes, int32_t n_nodes);
+/* UnaryElementWiseMayGrad::unary_ew (src/unary.rs:62-132) */
+int32_t cbm_unary_ew(cbm_device *d, cbm_buf in, const cb_node *fwd, int32_t n_fwd,
+                     const cb_node *grad, int32_t n_grad, cbm_buf *out);
+/* binary element-wise op with the retrieve + add_op pattern of README.md:96-122 */
+int32_t cbm_binary(cbm_device *d, int32_t op, cbm_buf lhs, cbm_buf rhs, cbm_buf *out);
+int32_t cbm_clear(cbm_device *d, cbm_buf b);                  /* ClearBuf::clear, eager like the reference */
+int32_t cbm_copy_slice(cbm_device *d, cbm_buf src, size_t src_off, cbm_buf dst, size_t dst_off, size_t n);
+int32_t cbm_clone_buf(cbm_device *d, cbm_buf src, cbm_buf *out);
+/* sum / mean of a buffer to a host scalar of the accumulation type (executes now) */
+int32_t cbm_sum(cbm_device *d, cbm_buf b, void *host_out);
+int32_t cbm_mean(cbm_device *d, cbm_buf b, void *host_out);
+
+/* Lazy: Run::run, ExecNow (src/modules/lazy.rs:143-198, src/features.rs:505-518) */
+int32_t cbm_run(cbm_device *d);
+int32_t cbm_exec_now(cbm_device *d, size_t begin, size_t end);   /* end = SIZE_MAX: to the last op */
+int32_t cbm_exec_last_n(cbm_device *d, size_t n);
+int32_t cbm_ops_count(cbm_device *d, size_t *n);
+int32_t cbm_alloc_later(cbm_device *d);
+int32_t cbm_set_lazy_enabled(cbm_device *d, int32_t enabled);
+/* op hint of recorded op i as reference source ("sin(x)"), "" if none (src/op_hint.rs:44-83) */
+int32_t cbm_op_hint_src(cbm_device *d, size_t i, char *out, size_t cap);
+/* replay through one captured CUDA graph instead of re-launching (src/devices/cuda/lazy.rs:31-49) */
+int32_t cbm_set_graph_replay(cbm_device *d, int32_t enabled);
+int32_t cbm_replay_kernel_nodes(cbm_device *d, size_t *n);
+
+/* Graph: Optimize (src/modules/graph.rs:79-113) */
+int32_t cbm_optimize_mem_graph(cbm_device *d);
+int32_t cbm_unary_fusing(cbm_device *d);
+/* cache traces of the current graph: flattened as [cache_idx, k, use_0..use_{k-1}]* */
+int32_t cbm_cache_traces(cbm_device *d, int64_t *out, size_t cap, size_t *written);
+
+/* Cached: Cursor + range (src/features.rs:68-111, src/range.rs:10-60) */
+int32_t cbm_cursor(cbm_device *d, uint64_t *cursor);
+int32_t cbm_set_cursor(cbm_device *d, uint64_t cursor);
+
+/* Autograd (src/buffer/impl_autograd.rs:20-197, src/modules/autograd/tape.rs:39-83) */
+int32_t cbm_backward(cbm_device *d, cbm_buf out);
+int32_t cbm_backward_with(cbm_device *d, cbm_buf out, const void *seed, size_t len);
+int32_t cbm_grad(cbm_device *d, cbm_buf b, cbm_buf *grad);     /* Buffer::grad: allocates (zeroed) on first use */
+int32_t cbm_zero_grad(cbm_device *d);
+int32_t cbm_set_grad_enabled(cbm_device *d, int32_t enabled);  /* Autograd::{enable,disable}_grad */
+
+/* ------------------------------------------- OptGraph without a device (a10) */
+/* src/modules/graph/opt_graph.rs:6-41 and opt_graph/optimize.rs:19-132 */
+typedef struct cb_optgraph cb_optgraph;
+int32_t cb_optgraph_create(cb_optgraph **out);
+int32_t cb_optgraph_destroy(cb_optgraph *g);
+int32_t cb_optgraph_add_leaf(cb_optgraph *g, size_t len, int64_t *idx);
+int32_t cb_optgraph_add_node(cb_optgraph *g, size_t len, const int64_t *deps, int32_t n_deps, int64_t *idx);
+int32_t cb_optgraph_set_skip(cb_optgraph *g, int64_t idx, int32_t skip);
+int32_t cb_optgraph_is_path_optimizable(cb_optgraph *g, int64_t idx, int32_t *out);
+int32_t cb_optgraph_trace_cache_path_raw(cb_optgraph *g, int64_t idx, int64_t *out, size_t cap, size_t *written);
+int32_t cb_optgraph_cache_traces(cb_optgraph *g, int64_t *out, size_t cap, size_t *written);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUSTOS_B200_H */
