@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — the headline benchmark of BASELINE.json on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--extra]
+
+Metric: achieved HBM GB/s of the fused 8-op unary chain on 2^28 f32
+per GPU.  One "step" = one pass of the fused chain kernel over the resident buffer (the
+buffers are 1 GiB each, far larger than the 126 MB L2, so no flush is needed between steps).
+`value` is device-timed (CUDA events on the library's stream) with inputs resident in HBM;
+`e2e` is the same work through the C-ABI with HOST buffers (pinned), H2D and D2H inside the
+timed region.  Weak scaling: every rank owns its own 2^28-element slice, no collective on the
+data path (max-over-ranks timing through torch.distributed/NCCL).
+
+`--impl reference` times the reference's CPU device (restated in oracle/, the Rust crate cannot
+be built here) on the host cores for the same metric/config on a bounded sample.
+Prints exactly one JSON line on stdout.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_ELEMS = 1 << 28
+BYTES_PER_ELEM = 8  # f32: 1 read + 1 write per element, whatever the chain length
+METRIC = "achieved HBM GB/s, fused 8-op unary chain, 2^28 f32 per GPU"
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel, from the committed ncu capture (or None)."""
+    p = ROOT / "profiles" / "roofline_traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get("chain8_f32_traffic_bytes")
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def wait_first(self, timeout: float):
+        t_end = time.time() + timeout
+        while self.proc and not self.rows and time.time() < t_end:
+            time.sleep(0.01)
+
+    def stop(self, t0: float, t1: float):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for (t, r) in self.rows if t0 + 0.1 <= t <= t1] or [r for (_, r) in self.rows]
+        for r in rows:
+            f = [c.strip() for c in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+                power.append(float(f[2]))
+                for name, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "power_w_max": max(power) if power else None, "samples": len(sm),
+                "how": "nvidia-smi -lms 50 while the timed kernel runs back to back (0.4 s before, the timed steps, 0.4 s after)"}
+
+
+def make_input(n: int, seed: int = 4) -> np.ndarray:
+    """x ~ U[-4, 4) f32, generated in chunks to bound host memory."""
+    rng = np.random.default_rng(seed)
+    out = np.empty(n, np.float32)
+    step = 1 << 24
+    for i in range(0, n, step):
+        m = min(step, n - i)
+        out[i:i + m] = rng.uniform(-4.0, 4.0, m).astype(np.float32)
+    return out
+
+
+def cpu_baseline_single(sample: int):
+    """The oracle (kind "port") on ONE host core: the reference CPU device is single threaded."""
+    from custos_b200.workloads import CHAIN8
+    from oracle import oracle as orc
+    x = make_input(sample)
+    orc.apply_chain(CHAIN8, orc.F32, x[:1 << 16])
+    t = time.perf_counter()
+    orc.apply_chain(CHAIN8, orc.F32, x)
+    dt = time.perf_counter() - t
+    return {"value": sample * BYTES_PER_ELEM / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+            "sample": f"fused CHAIN8 over 2^{int(np.log2(sample))} f32 (U[-4,4), seed 4), oracle/ C port of the reference "
+                      f"CPU device, single thread as in the reference; {sample / dt / 1e6:.1f} M elem/s"}
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from custos_b200.workloads import CHAIN8
+    from oracle import oracle as orc
+    cores = os.cpu_count() or 1
+    sample = 1 << 26
+    x = make_input(sample)
+    for _ in range(max(args.warmup, 1)):
+        orc.apply_chain(CHAIN8, orc.F32, x[:1 << 22], threads=cores)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        orc.apply_chain(CHAIN8, orc.F32, x, threads=cores)
+    dt = (time.perf_counter() - t) / args.steps
+    val = sample * BYTES_PER_ELEM / dt / 1e9
+    desc = (f"each step = fused CHAIN8 over a 2^26-element sample of the 2^28 f32 workload, oracle/ C port of the "
+            f"reference CPU device (the Rust crate cannot be built here), split over {cores} host threads "
+            f"(the reference itself is single threaded)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3 * (N_ELEMS / sample), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "chain8_f32_2^28_per_gpu", "sample_elems": sample, "elements_per_s": sample / dt},
+        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from custos_b200 import _native as N
+    from custos_b200.build import build
+    from custos_b200.raw import RawDevice
+    from custos_b200.workloads import CHAIN8
+
+    build()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    dev = RawDevice(local_rank)
+    n = args.elems
+    nbytes = n * 4
+    chain = dev.compile(CHAIN8, N.F32)
+
+    # pinned host buffers: the user's data lives on the host in the e2e path
+    h_in, h_out = dev.host_alloc(nbytes), dev.host_alloc(nbytes)
+    import ctypes
+    host_in = np.ctypeslib.as_array((ctypes.c_float * n).from_address(h_in))
+    host_out = np.ctypeslib.as_array((ctypes.c_float * n).from_address(h_out))
+    host_in[:] = make_input(n, seed=4 + rank)
+    d_in, d_out = dev.alloc(nbytes, zero=False), dev.alloc(nbytes, zero=False)
+    dev.h2d_async(d_in, h_in, nbytes)
+    dev.sync()
+
+    # ---------------------------------------------------------------- device-resident timing
+    def spin(seconds: float):
+        """untimed steps of the same kernel: keeps the GPU under the same load around the timed
+        region so that the nvidia-smi samples (50 ms period) describe it"""
+        t_end = time.time() + seconds
+        while time.time() < t_end:
+            for _ in range(20):
+                dev.apply(chain, d_in, d_out, n)
+            dev.sync()
+
+    sampler = ClockSampler(local_rank)
+    for _ in range(args.warmup):
+        dev.apply(chain, d_in, d_out, n)
+    dev.sync()
+    sampler.wait_first(2.0)
+    t_load0 = time.time()
+    spin(0.4)
+    barrier()
+    launches0 = dev.launches
+    ev0, ev1 = dev.event(), dev.event()
+    ev0.record()
+    for _ in range(args.steps):
+        dev.apply(chain, d_in, d_out, n)
+    ev1.record()
+    ev1.sync()
+    dev.sync()
+    launches = dev.launches - launches0
+    barrier()
+    spin(0.4)
+    t_load1 = time.time()
+    ms_total = max_over_ranks(ev0.elapsed_ms(ev1))
+    clocks = sampler.stop(t_load0, t_load1)
+    ms_per_step = ms_total / args.steps
+    value = world * n * BYTES_PER_ELEM / (ms_per_step * 1e-3) / 1e9
+
+    # ---------------------------------------------------------------- end to end (host buffers)
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        dev.h2d_async(d_in, h_in, nbytes)
+        dev.apply(chain, d_in, d_out, n)
+        dev.d2h_async(h_out, d_out, nbytes)
+    dev.sync()
+    barrier()
+    ev0.record()
+    for _ in range(e2e_steps):
+        dev.h2d_async(d_in, h_in, nbytes)
+        dev.apply(chain, d_in, d_out, n)
+        dev.d2h_async(h_out, d_out, nbytes)
+    ev1.record()
+    ev1.sync()
+    dev.sync()
+    barrier()
+    e2e_ms = max_over_ranks(ev0.elapsed_ms(ev1)) / e2e_steps
+    e2e_value = world * n * BYTES_PER_ELEM / (e2e_ms * 1e-3) / 1e9
+
+    # sanity: the timed kernel really computed the chain (sampled check against the oracle)
+    check = None
+    if rank == 0:
+        from oracle import oracle as orc
+        idx = np.random.default_rng(0).integers(0, n, 4096)
+        want = orc.apply_chain(CHAIN8, orc.F32, host_in[idx])
+        got = host_out[idx]
+        check = float(np.max(np.abs(got.astype(np.float64) - want.astype(np.float64))))
+
+    peak, peak_src = measured_peak()
+    achieved = n * BYTES_PER_ELEM / (ms_per_step * 1e-3) / 1e9  # per GPU, the dominant (only) kernel
+    out = {
+        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "chain8_f32_2^28_per_gpu" if n == N_ELEMS else f"chain8_f32_{n}_per_gpu",
+                   "chain": "add(1) mul(0.5) exp sin mul(2) add(1) tanh neg", "elements_per_gpu": n,
+                   "elements_per_s": world * n / (ms_per_step * 1e-3), "l2": "inputs (1 GiB in + 1 GiB out) larger than L2",
+                   "parallelism": f"slice{world}", "sampled_check_max_abs_err": check},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic(), "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
+                     "kernel": "cb_apply_vec (NVRTC, fused CHAIN8)", "algorithmic_bytes_per_launch": n * BYTES_PER_ELEM},
+        "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+                "ms_per_step": e2e_ms, "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if rank == 0 and world == 1:
+        out["cpu_baseline"] = cpu_baseline_single(1 << 25)
+    if rank == 0 and args.extra:
+        out["extra"] = extra_workloads(dev, n)
+    dev.host_free(h_in)
+    dev.host_free(h_out)
+    dev.close()
+    if world > 1:
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+def extra_workloads(dev, n):
+    """The other rows of BASELINE.md §4 (not bench lines of the contract; for DESIGN.md / profiles)."""
+    from custos_b200 import _native as N
+    from custos_b200.workloads import CHAIN8, CHAIN8_GRADS, CHEAP8
+    peak, _ = measured_peak()
+    res = {}
+
+    def timeit(fn, reps=20, warm=5):
+        for _ in range(warm):
+            fn()
+        dev.sync()
+        e0, e1 = dev.event(), dev.event()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        e1.sync()
+        return e0.elapsed_ms(e1) / reps
+
+    a, b, c = dev.alloc(n * 4), dev.alloc(n * 4), dev.alloc(n * 4)
+    dev.fill(N.F32, a, n, 0.5)
+    dev.fill(N.F32, b, n, 0.25)
+
+    def row(name, ms, bytes_per_elem, elems=n):
+        gbs = elems * bytes_per_elem / (ms * 1e-3) / 1e9
+        res[name] = {"ms": ms, "GB/s": gbs, "frac_of_measured_peak": gbs / peak, "elements_per_s": elems / (ms * 1e-3)}
+
+    cheap = dev.compile(CHEAP8, N.F32)
+    row("cheap8_f32", timeit(lambda: dev.apply(cheap, a, c, n)), 8)
+    chain = dev.compile(CHAIN8, N.F32)
+    row("chain8_f32", timeit(lambda: dev.apply(chain, a, c, n)), 8)
+    chain16 = dev.compile(CHAIN8, N.F16)
+    row("chain8_f16", timeit(lambda: dev.apply(chain16, a, c, n)), 4)
+    row("binary_add_f32", timeit(lambda: dev.binary(N.F32, N.BIN_ADD, a, b, c, n)), 12)
+    row("binary_mul_f32", timeit(lambda: dev.binary(N.F32, N.BIN_MUL, a, b, c, n)), 12)
+    g = dev.compile(CHAIN8_GRADS[3], N.F32, N.KERNEL_UNARY_GRAD)
+    row("unary_grad_cos_f32", timeit(lambda: dev.unary_grad(g, a, c, b, n)), 16)
+    row("clear_f32", timeit(lambda: dev.clear(N.F32, c, n)), 4)
+    row("copy_f32", timeit(lambda: dev.copy(N.F32, c, 0, a, 0, n)), 8)
+    s = dev.alloc(64)
+    row("sum_f32", timeit(lambda: dev.sum_into(N.F32, a, n, s)), 4)
+    for p in (a, b, c, s):
+        dev.free(p)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--elems", type=int, default=N_ELEMS, help="elements per GPU (default 2^28, the BASELINE config)")
+    ap.add_argument("--extra", action="store_true", help="also time the other BASELINE.md rows (adds an 'extra' object)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

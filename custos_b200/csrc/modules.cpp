@@ -1,0 +1,1028 @@
+// modules.cpp — custos' module stack (Base, Cached, Lazy, Graph, Autograd) restated in C++
+// around the CUDA device, exported through the cbm_* part of the C ABI.
+//
+// In the reference the stack is a compile-time nest of mixins, `CUDA<Graph<Lazy<Base>>>`;
+// here it is one device object configured by a bit mask, because the composition has to be
+// driven through a C ABI.  The observable behaviour follows the reference module by module:
+//
+//   Base      eager: add_op runs the operation at once, retrieve allocates
+//             (src/modules/base.rs:53-62,118-129)
+//   Cached    the k-th retrieve after a cursor reset returns the k-th allocation
+//             (src/modules/cached.rs:173-229, src/range.rs:35-48)
+//   Lazy      retrieve hands out ids and defers the allocation, add_op records, run()
+//             allocates and replays (src/modules/lazy.rs:93-107,143-198,325-387)
+//   Graph     every retrieve adds a node (len, parent nodes); cache traces drive buffer
+//             aliasing and unary fusing (src/modules/graph.rs:79-127,159-195,
+//             src/modules/lazy/optimization.rs:4-95, src/devices/fusing.rs:41-92)
+//   Autograd  requires-grad propagation, a tape of grad functions replayed in reverse,
+//             gradient buffers allocated (zeroed) on first use (src/modules/autograd.rs:108-281,
+//             autograd/tape.rs:30-83, autograd/gradients.rs:110-124, buffer/impl_autograd.rs:20-56)
+//
+// Deliberate differences from the reference (each keeps the CPU-visible results):
+//   * run() does not launch every op eagerly AND replay a captured graph;
+//     with graph replay enabled the ops are captured once and only replayed.
+//   * backward() seeds the output gradient with a device-side fill instead of a host vector
+//     of ones (impl_autograd.rs:32).
+//   * optimize_mem_graph keeps the deferred allocation of buffers that are on no cache trace
+//     (the reference drains and forgets them, lazy/optimization.rs:11, and run() then fails).
+//   * unary_fusing fuses maximal runs of unary-hinted ops on a trace and leaves other ops of
+//     the trace alone (the reference turns a trace that contains a non-unary op into no-ops,
+//     lazy/optimization.rs:77-91); on pure unary traces — all the reference tests — both agree.
+//   * aliasing / fusing skip buffers whose dtype or length differ instead of panicking later.
+#include <algorithm>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <unordered_map>
+#include <unordered_set>
+
+#include "device.h"
+#include "expr.h"
+#include "optgraph.h"
+
+using namespace cb;
+
+int32_t cb_flatten_traces(const std::vector<cb::CacheTrace> &traces, int64_t *out, size_t cap, size_t *written);
+
+namespace {
+
+// what Lazy::buffers / Autograd::no_grads_pool hold: id -> shallow view of the storage
+struct Entry {
+    uint64_t ptr = 0;
+    size_t len = 0;
+    int32_t dtype = CB_F32;
+};
+
+// a user visible Buffer
+struct Handle {
+    uint64_t id = 0;   // HasId::id(): device address for eager buffers (cuda_ptr.rs:42-50), cursor for lazy ones
+    size_t len = 0;
+    int32_t dtype = CB_F32;
+    uint64_t ptr = 0;  // storage owned by (or lent to) this handle; 0 for lazily retrieved buffers
+    bool lazy = false;
+    bool owned = false;  // freed on drop (AllocFlag::None); cached and gradient buffers are not
+};
+
+enum class OpKind { NoOp, Apply, UnaryGrad, Binary };
+
+// Operation (src/modules/lazy/lazy_graph.rs:8-12): argument ids + what to launch + the op hint
+struct Op {
+    OpKind kind = OpKind::NoOp;
+    std::vector<uint64_t> arg_ids;
+    int32_t dtype = CB_F32;
+    cb_expr *expr = nullptr;
+    int32_t binop = 0;
+    bool unary_hint = false;       // OpHint::Unary (src/op_hint.rs:5-11)
+    bool fused = false;            // OpHint::UnaryFused
+    std::vector<cb_node> hint;     // the closure of the hint, as IR
+};
+
+// a grad function on the tape: the closure of unary_ew (src/unary.rs:118-128)
+struct GradOp {
+    uint64_t buf_id = 0, out_id = 0;
+    int32_t dtype = CB_F32;
+    cb_expr *grad_expr = nullptr;
+};
+
+struct Deferred {
+    uint64_t id;
+    size_t len;
+    int32_t dtype;
+};
+
+struct CacheSlot {
+    uint64_t ptr;
+    size_t len;
+    int32_t dtype;
+};
+
+}  // namespace
+
+struct cbm_device {
+    cb_device *raw = nullptr;
+    uint32_t mods = 0;
+    int32_t dtype = CB_F32;  // the module's `T` (Lazy<Mods, T = f32>, Graph<Mods, T = f32>)
+
+    uint64_t next_handle = 1;
+    std::unordered_map<uint64_t, Handle> handles;
+    std::unordered_map<uint64_t, Entry> buffers;  // id -> storage
+    std::vector<uint64_t> lazy_allocs;            // memory owned by the Lazy module
+
+    // Cursor (features.rs:68-111): shared by Cached / Lazy, read by Graph
+    uint64_t cursor = 0;
+    std::unordered_map<uint64_t, CacheSlot> cache;  // Cached: cursor -> allocation
+
+    // Lazy
+    bool lazy_enabled = true;
+    std::vector<Deferred> alloc_later;
+    std::unordered_set<uint64_t> allocated_ids;
+    std::vector<Op> ops;
+    std::unordered_map<uint64_t, size_t> op_of_id;  // retrieved buffer id -> index of the op writing it
+    bool replay_enabled = false;
+    cb_graph *replay = nullptr;
+    bool replay_valid = false;
+
+    // Graph (graph_translator.rs:9-18)
+    OptGraph graph;
+    std::unordered_map<uint64_t, size_t> buf_id_to_idx;
+    std::unordered_map<size_t, uint64_t> idx_to_buf_id;
+    std::unordered_map<size_t, uint64_t> idx_to_cursor;
+    std::unordered_set<uint64_t> contains_ids;
+
+    // Autograd
+    bool grad_enabled = true;
+    std::vector<GradOp> tape;
+    std::unordered_map<uint64_t, Entry> grads;          // Gradients::grads_pool
+    std::unordered_map<uint64_t, uint64_t> grad_handle; // id -> handle lent to the user
+    std::unordered_map<uint64_t, bool> requires_grad;   // Gradients::buf_requires_grad
+
+    bool has(uint32_t m) const { return (mods & m) != 0; }
+    bool recording() const { return has(CBM_LAZY) && lazy_enabled; }
+    void invalidate_replay() { replay_valid = false; }
+
+    Handle *handle(cbm_buf b)
+    {
+        auto it = handles.find(b);
+        return it == handles.end() ? nullptr : &it->second;
+    }
+    // Buffer::replace(): the storage currently registered under the buffer's id
+    const Entry *resolve(uint64_t id) const
+    {
+        auto it = buffers.find(id);
+        return it == buffers.end() ? nullptr : &it->second;
+    }
+    std::unordered_map<uint64_t, int> id_refs;  // live handles per id (cached slots are handed out repeatedly)
+    cbm_buf new_handle(const Handle &h)
+    {
+        const cbm_buf b = next_handle++;
+        handles[b] = h;
+        id_refs[h.id]++;
+        return b;
+    }
+};
+
+namespace {
+
+#define GET_HANDLE(var, d, b)                                                                      \
+    Handle *var = (d)->handle(b);                                                                  \
+    if (!var) return fail(CB_ERR_INVALID_ARG, "%s: unknown buffer handle %llu", __func__, (unsigned long long)(b))
+
+int32_t alloc_zeroed(cbm_device *d, int32_t dtype, size_t len, uint64_t *ptr)
+{
+    if (len == 0) return fail(CB_ERR_ZERO_LENGTH, "zero length buffer");  // DeviceError::ZeroLengthBuffer
+    return cb_alloc(d->raw, len * dtype_size(dtype), 1, ptr);
+}
+
+// Graph::on_new_buffer (graph.rs:115-127) + Lazy::on_new_buffer (lazy.rs:200-214)
+void on_new_buffer(cbm_device *d, const Handle &h)
+{
+    if (d->has(CBM_GRAPH)) {
+        d->buf_id_to_idx[h.id] = d->graph.size();
+        d->graph.add_leaf(h.len);
+    }
+    d->buffers[h.id] = Entry{h.ptr, h.len, h.dtype};
+    if (d->has(CBM_AUTOGRAD)) d->requires_grad.emplace(h.id, false);
+}
+
+// Lazy::alloc_later (lazy.rs:175-181 + the callback at :345-380)
+int32_t run_alloc_later(cbm_device *d)
+{
+    std::vector<Deferred> todo;
+    todo.swap(d->alloc_later);
+    for (const Deferred &a : todo) {
+        if (d->allocated_ids.count(a.id)) continue;
+        if (d->buffers.count(a.id)) return fail(CB_ERR_STATE, "IDs collided! Maybe pointing address already occupied this ID.");
+        uint64_t p = 0;
+        CB_TRY(alloc_zeroed(d, a.dtype, a.len, &p));
+        d->lazy_allocs.push_back(p);
+        d->allocated_ids.insert(a.id);
+        d->buffers[a.id] = Entry{p, a.len, a.dtype};
+    }
+    return CB_OK;
+}
+
+// runs one recorded operation now; every argument is looked up by id (any_op.rs:112-124)
+int32_t call_op(cbm_device *d, const Op &op)
+{
+    if (op.kind == OpKind::NoOp) return CB_OK;
+    const Entry *arg[3] = {nullptr, nullptr, nullptr};
+    for (size_t i = 0; i < op.arg_ids.size() && i < 3; i++) {
+        arg[i] = d->resolve(op.arg_ids[i]);
+        if (!arg[i]) return fail(CB_ERR_INVALID_LAZY_BUF, "InvalidLazyBuf: buffer id %llu is not alive",
+                                 (unsigned long long)op.arg_ids[i]);
+    }
+    switch (op.kind) {
+    case OpKind::Apply:  // args: (out, in)
+        return cb_apply(d->raw, op.expr, arg[1]->ptr, arg[0]->ptr, std::min(arg[0]->len, arg[1]->len));
+    case OpKind::UnaryGrad:  // args: (lhs, lhs_grad, out)
+        return cb_unary_grad(d->raw, op.expr, arg[0]->ptr, arg[1]->ptr, arg[2]->ptr, arg[0]->len);
+    case OpKind::Binary:  // args: (lhs, rhs, out)
+        return cb_binary(d->raw, op.dtype, op.binop, arg[0]->ptr, arg[1]->ptr, arg[2]->ptr, arg[2]->len);
+    default: return CB_OK;
+    }
+}
+
+// AddOperation::add_op: Lazy records (lazy.rs:93-107), everything else runs now (base.rs:53-62)
+int32_t add_op(cbm_device *d, Op op)
+{
+    // "each parent (id) must be unique" (lazy_graph.rs:112-128)
+    for (size_t i = 0; i < op.arg_ids.size(); i++)
+        for (size_t j = i + 1; j < op.arg_ids.size(); j++)
+            if (op.arg_ids[i] == op.arg_ids[j])
+                return fail(CB_ERR_INVALID_ARG, "each parent (id) must be unique");
+    if (d->recording()) {
+        d->ops.push_back(std::move(op));
+        d->invalidate_replay();
+        return CB_OK;
+    }
+    return call_op(d, op);
+}
+
+int32_t compile_one(cbm_device *d, int32_t dtype, int32_t kind, const cb_node *nodes, int32_t n, cb_expr **out)
+{
+    const cb_node *progs[1] = {nodes};
+    const int32_t counts[1] = {n};
+    return cb_expr_compile(d->raw, dtype, kind, progs, counts, 1, out);
+}
+
+// Retriever::retrieve through the module stack
+int32_t retrieve(cbm_device *d, int32_t dtype, size_t len, const cbm_buf *parents, int32_t n_parents, cbm_buf *out)
+{
+    if (!valid_dtype(dtype)) return fail(CB_ERR_INVALID_ARG, "invalid dtype %d", dtype);
+    if (len == 0) return fail(CB_ERR_ZERO_LENGTH, "retrieve: zero length buffer");
+    std::vector<uint64_t> parent_ids;
+    bool any_requires_grad = false;
+    for (int32_t i = 0; i < n_parents; i++) {
+        GET_HANDLE(p, d, parents[i]);
+        parent_ids.push_back(p->id);
+        auto it = d->requires_grad.find(p->id);
+        any_requires_grad = any_requires_grad || (it != d->requires_grad.end() && it->second);
+    }
+
+    Handle h;
+    h.len = len;
+    h.dtype = dtype;
+    const uint64_t used_cursor = d->cursor;
+    if (d->has(CBM_LAZY)) {
+        // Lazy::retrieve: no allocation, the id is the cursor (lazy.rs:325-387)
+        h.id = d->cursor;
+        h.lazy = true;
+        d->alloc_later.push_back(Deferred{h.id, len, dtype});
+        d->cursor++;
+    } else if (d->has(CBM_CACHED)) {
+        // CachedModule::retrieve_entry (cached.rs:173-229)
+        auto it = d->cache.find(d->cursor);
+        if (it == d->cache.end()) {
+            uint64_t p = 0;
+            CB_TRY(alloc_zeroed(d, dtype, len, &p));
+            it = d->cache.emplace(d->cursor, CacheSlot{p, len, dtype}).first;
+        } else if (it->second.len * dtype_size(it->second.dtype) < len * dtype_size(dtype)) {
+            return fail(CB_ERR_SHAPE, "cached buffer at cursor %llu is smaller than the requested one",
+                        (unsigned long long)d->cursor);
+        }
+        h.ptr = it->second.ptr;
+        h.id = h.ptr;
+        d->cursor++;
+        d->buffers[h.id] = Entry{h.ptr, len, dtype};
+    } else {
+        // Base::retrieve = device.alloc (base.rs:118-129); zeroed like the CPU device
+        CB_TRY(alloc_zeroed(d, dtype, len, &h.ptr));
+        h.id = h.ptr;
+        h.owned = true;
+        d->buffers[h.id] = Entry{h.ptr, len, dtype};
+    }
+
+    if (d->has(CBM_GRAPH) && !d->contains_ids.count(used_cursor)) {
+        // Graph::retrieve_inner (graph.rs:159-195)
+        d->contains_ids.insert(used_cursor);
+        std::vector<size_t> deps;
+        for (uint64_t pid : parent_ids) {
+            auto it = d->buf_id_to_idx.find(pid);
+            if (it == d->buf_id_to_idx.end())
+                return fail(CB_ERR_GRAPH_OPTIMIZATION, "parent buffer id %llu is unknown to the graph", (unsigned long long)pid);
+            deps.push_back(it->second);
+        }
+        const size_t idx = d->graph.size();
+        d->buf_id_to_idx[h.id] = idx;
+        d->idx_to_buf_id[idx] = h.id;
+        d->idx_to_cursor[idx] = used_cursor;
+        d->graph.add_node(len, std::move(deps));
+    }
+    if (d->has(CBM_AUTOGRAD)) d->requires_grad[h.id] = any_requires_grad;  // autograd.rs:122-128
+    *out = d->new_handle(h);
+    return CB_OK;
+}
+
+// Gradients::get_mut / get_ref: allocate (zeroed) on first use (gradients.rs:94-124, borrow_cache.rs:50-78)
+int32_t grad_entry(cbm_device *d, uint64_t id, size_t len, int32_t dtype, Entry **out)
+{
+    auto it = d->grads.find(id);
+    if (it == d->grads.end()) {
+        uint64_t p = 0;
+        CB_TRY(alloc_zeroed(d, dtype, len, &p));
+        it = d->grads.emplace(id, Entry{p, len, dtype}).first;
+    }
+    *out = &it->second;
+    return CB_OK;
+}
+
+int32_t run_ops(cbm_device *d)
+{
+    for (const Op &op : d->ops) CB_TRY(call_op(d, op));
+    return CB_OK;
+}
+
+void free_replay(cbm_device *d)
+{
+    if (d->replay) cb_graph_destroy(d->replay);
+    d->replay = nullptr;
+    d->replay_valid = false;
+}
+
+}  // namespace
+
+// ===================================================================== device
+extern "C" int32_t cbm_device_create(int32_t ordinal, uint32_t modules, int32_t dtype, cbm_device **out)
+{
+    CB_CHECK_ARG(out, "out is null");
+    *out = nullptr;
+    if (!valid_dtype(dtype)) return fail(CB_ERR_INVALID_ARG, "invalid dtype %d", dtype);
+    if (modules & ~(CBM_CACHED | CBM_LAZY | CBM_GRAPH | CBM_AUTOGRAD)) return fail(CB_ERR_INVALID_ARG, "unknown module bits");
+    if ((modules & CBM_GRAPH) && !(modules & (CBM_LAZY | CBM_CACHED)))
+        return fail(CB_ERR_INVALID_ARG, "Graph needs a Cursor: stack it on Lazy or Cached (graph.rs:159-176)");
+    std::unique_ptr<cbm_device> d(new cbm_device());
+    d->mods = modules;
+    d->dtype = dtype;
+    CB_TRY(cb_device_create(ordinal, &d->raw));
+    *out = d.release();
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_device_destroy(cbm_device *d)
+{
+    if (!d) return CB_OK;
+    free_replay(d);
+    for (auto &kv : d->handles)
+        if (kv.second.owned && kv.second.ptr) cb_free(d->raw, kv.second.ptr);
+    for (uint64_t p : d->lazy_allocs) cb_free(d->raw, p);
+    for (auto &kv : d->cache) cb_free(d->raw, kv.second.ptr);
+    for (auto &kv : d->grads) cb_free(d->raw, kv.second.ptr);
+    cb_device_destroy(d->raw);
+    delete d;
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_device_raw(cbm_device *d, cb_device **raw)
+{
+    CB_CHECK_ARG(d && raw, "null argument");
+    *raw = d->raw;
+    return CB_OK;
+}
+
+// ===================================================================== buffers
+extern "C" int32_t cbm_buffer_new(cbm_device *d, int32_t dtype, size_t len, cbm_buf *out)
+{
+    CB_CHECK_ARG(d && out, "null argument");
+    if (!valid_dtype(dtype)) return fail(CB_ERR_INVALID_ARG, "invalid dtype %d", dtype);
+    Handle h;
+    h.len = len;
+    h.dtype = dtype;
+    h.owned = true;
+    CB_TRY(alloc_zeroed(d, dtype, len, &h.ptr));  // Buffer::new allocates at once, also under Lazy
+    h.id = h.ptr;
+    on_new_buffer(d, h);
+    *out = d->new_handle(h);
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_buffer_from_host(cbm_device *d, int32_t dtype, const void *data, size_t len, cbm_buf *out)
+{
+    CB_CHECK_ARG(d && out && data, "null argument");
+    if (!valid_dtype(dtype)) return fail(CB_ERR_INVALID_ARG, "invalid dtype %d", dtype);
+    if (len == 0) return fail(CB_ERR_ZERO_LENGTH, "zero length buffer");
+    Handle h;
+    h.len = len;
+    h.dtype = dtype;
+    h.owned = true;
+    CB_TRY(cb_alloc(d->raw, len * dtype_size(dtype), 0, &h.ptr));  // alloc_from_slice (cuda.rs:124-137)
+    int32_t rc = cb_h2d(d->raw, h.ptr, data, len * dtype_size(dtype));
+    if (rc != CB_OK) {
+        cb_free(d->raw, h.ptr);
+        return rc;
+    }
+    h.id = h.ptr;
+    on_new_buffer(d, h);
+    *out = d->new_handle(h);
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_buffer_drop(cbm_device *d, cbm_buf b)
+{
+    CB_CHECK_ARG(d, "null device");
+    GET_HANDLE(h, d, b);
+    // the registered shallow copy goes away with the buffer: recorded ops that still name the
+    // id fail with InvalidLazyBuf at run() (lazy.rs:624-640)
+    bool is_grad_view = false;
+    for (auto &kv : d->grad_handle) is_grad_view = is_grad_view || kv.second == b;
+    const bool last_ref = --d->id_refs[h->id] <= 0;
+    if (last_ref) d->id_refs.erase(h->id);
+    if (!is_grad_view && last_ref) d->buffers.erase(h->id);
+    if (h->owned && h->ptr) CB_TRY(cb_free(d->raw, h->ptr));
+    d->handles.erase(b);
+    d->invalidate_replay();
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_buffer_len(cbm_device *d, cbm_buf b, size_t *len)
+{
+    CB_CHECK_ARG(d && len, "null argument");
+    GET_HANDLE(h, d, b);
+    *len = h->len;
+    return CB_OK;
+}
+
+static int32_t storage_of(cbm_device *d, const Handle *h, Entry *out)
+{
+    if (!h->lazy && h->ptr && !d->resolve(h->id)) {  // gradient views and the like
+        *out = Entry{h->ptr, h->len, h->dtype};
+        return CB_OK;
+    }
+    const Entry *e = d->resolve(h->id);
+    if (!e) return fail(CB_ERR_INVALID_LAZY_BUF, "buffer id %llu has no storage yet (lazy buffer before run()/alloc_later())",
+                        (unsigned long long)h->id);
+    *out = *e;
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_buffer_read(cbm_device *d, cbm_buf b, void *host_out, size_t len)
+{
+    CB_CHECK_ARG(d && host_out, "null argument");
+    GET_HANDLE(h, d, b);
+    Entry e;
+    CB_TRY(storage_of(d, h, &e));
+    if (len > e.len) return fail(CB_ERR_SHAPE, "read of %zu elements from a buffer of %zu", len, e.len);
+    return cb_d2h(d->raw, host_out, e.ptr, len * dtype_size(h->dtype));
+}
+
+extern "C" int32_t cbm_buffer_write(cbm_device *d, cbm_buf b, const void *host_in, size_t len)
+{
+    CB_CHECK_ARG(d && host_in, "null argument");
+    GET_HANDLE(h, d, b);
+    Entry e;
+    CB_TRY(storage_of(d, h, &e));
+    if (len > e.len) return fail(CB_ERR_SHAPE, "write of %zu elements into a buffer of %zu", len, e.len);
+    return cb_h2d(d->raw, e.ptr, host_in, len * dtype_size(h->dtype));
+}
+
+extern "C" int32_t cbm_buffer_ptr(cbm_device *d, cbm_buf b, uint64_t *dptr)
+{
+    CB_CHECK_ARG(d && dptr, "null argument");
+    GET_HANDLE(h, d, b);
+    const Entry *e = d->resolve(h->id);
+    *dptr = e ? e->ptr : h->ptr;
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_buffer_id(cbm_device *d, cbm_buf b, uint64_t *id)
+{
+    CB_CHECK_ARG(d && id, "null argument");
+    GET_HANDLE(h, d, b);
+    *id = h->id;
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_buffer_require_grad(cbm_device *d, cbm_buf b)
+{
+    CB_CHECK_ARG(d, "null device");
+    GET_HANDLE(h, d, b);
+    d->requires_grad[h->id] = true;
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_buffer_requires_grad(cbm_device *d, cbm_buf b, int32_t *flag)
+{
+    CB_CHECK_ARG(d && flag, "null argument");
+    GET_HANDLE(h, d, b);
+    auto it = d->requires_grad.find(h->id);
+    *flag = (it != d->requires_grad.end() && it->second) ? 1 : 0;
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_buffer_checkpoint(cbm_device *d, cbm_buf b)
+{
+    CB_CHECK_ARG(d, "null device");
+    GET_HANDLE(h, d, b);
+    if (!d->has(CBM_GRAPH)) return CB_OK;  // set_checkpoint_buffer passes down to nothing
+    auto it = d->buf_id_to_idx.find(h->id);
+    if (it == d->buf_id_to_idx.end()) return fail(CB_ERR_GRAPH_OPTIMIZATION, "buffer is unknown to the graph");
+    d->graph.node(it->second).skip = true;  // graph.rs:255-259
+    return CB_OK;
+}
+
+// ===================================================================== operations
+extern "C" int32_t cbm_retrieve(cbm_device *d, int32_t dtype, size_t len, const cbm_buf *parents, int32_t n_parents,
+                                cbm_buf *out)
+{
+    CB_CHECK_ARG(d && out && (n_parents == 0 || parents) && n_parents >= 0, "bad argument");
+    return retrieve(d, dtype, len, parents, n_parents, out);
+}
+
+extern "C" int32_t cbm_apply_fn(cbm_device *d, cbm_buf in, const cb_node *nodes, int32_t n_nodes, cbm_buf *out)
+{
+    CB_CHECK_ARG(d && out, "null argument");
+    GET_HANDLE(hin, d, in);
+    const int32_t dtype = hin->dtype;
+    const uint64_t in_id = hin->id;
+    const size_t len = hin->len;
+    cb_expr *e = nullptr;
+    CB_TRY(compile_one(d, dtype, CB_KERNEL_APPLY, nodes, n_nodes, &e));
+    // let mut out = self.retrieve(buf.len(), buf); self.add_op((&mut out, buf), ..); self.set_op_hint(unary(f))
+    // (src/devices/cuda/ops.rs:134-140)
+    cbm_buf ob = 0;
+    CB_TRY(retrieve(d, dtype, len, &in, 1, &ob));
+    const uint64_t out_id = d->handle(ob)->id;
+    Op op;
+    op.kind = OpKind::Apply;
+    op.arg_ids = {out_id, in_id};
+    op.dtype = dtype;
+    op.expr = e;
+    if (d->recording()) {  // Lazy::set_op_hint (lazy.rs:136-143); Base ignores hints (base.rs:86)
+        op.unary_hint = true;
+        op.hint.assign(nodes, nodes + n_nodes);
+        d->op_of_id[out_id] = d->ops.size();
+    }
+    int32_t rc = add_op(d, std::move(op));
+    if (rc != CB_OK) return rc;
+    *out = ob;
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_add_unary_grad(cbm_device *d, cbm_buf lhs, cbm_buf lhs_grad, cbm_buf out_grad, const cb_node *nodes,
+                                      int32_t n_nodes)
+{
+    CB_CHECK_ARG(d, "null device");
+    GET_HANDLE(hl, d, lhs);
+    GET_HANDLE(hg, d, lhs_grad);
+    GET_HANDLE(ho, d, out_grad);
+    if (hl->dtype != hg->dtype || hl->dtype != ho->dtype) return fail(CB_ERR_INVALID_ARG, "dtype mismatch");
+    if (hg->len < hl->len || ho->len < hl->len) return fail(CB_ERR_SHAPE, "gradient buffers are shorter than lhs");
+    cb_expr *e = nullptr;
+    CB_TRY(compile_one(d, hl->dtype, CB_KERNEL_UNARY_GRAD, nodes, n_nodes, &e));
+    Op op;
+    op.kind = OpKind::UnaryGrad;
+    op.arg_ids = {hl->id, hg->id, ho->id};  // (lhs, lhs_grad, out): src/devices/cuda/ops.rs:198
+    op.dtype = hl->dtype;
+    op.expr = e;
+    return add_op(d, std::move(op));
+}
+
+extern "C" int32_t cbm_unary_ew(cbm_device *d, cbm_buf in, const cb_node *fwd, int32_t n_fwd, const cb_node *grad,
+                                int32_t n_grad, cbm_buf *out)
+{
+    CB_CHECK_ARG(d && out, "null argument");
+    GET_HANDLE(hin, d, in);
+    const int32_t dtype = hin->dtype;
+    const uint64_t in_id = hin->id;
+    // the grad closure is validated up front even when it is never recorded
+    CB_TRY(expr_validate(dtype, CB_KERNEL_UNARY_GRAD, grad, n_grad));
+    CB_TRY(cbm_apply_fn(d, in, fwd, n_fwd, out));
+    // add_grad_fn: a no-op without Autograd or with gradients disabled (autograd.rs:248-258)
+    if (!d->has(CBM_AUTOGRAD) || !d->grad_enabled) return CB_OK;
+    GradOp g;
+    g.buf_id = in_id;
+    g.out_id = d->handle(*out)->id;
+    g.dtype = dtype;
+    CB_TRY(compile_one(d, dtype, CB_KERNEL_UNARY_GRAD, grad, n_grad, &g.grad_expr));
+    d->tape.push_back(g);
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_binary(cbm_device *d, int32_t op, cbm_buf lhs, cbm_buf rhs, cbm_buf *out)
+{
+    CB_CHECK_ARG(d && out, "null argument");
+    CB_CHECK_ARG(op >= CB_BIN_ADD && op <= CB_BIN_DIV, "bad binary op");
+    GET_HANDLE(hl, d, lhs);
+    GET_HANDLE(hr, d, rhs);
+    if (hl->dtype != hr->dtype) return fail(CB_ERR_INVALID_ARG, "dtype mismatch");
+    if (hl->len != hr->len) return fail(CB_ERR_SHAPE, "length mismatch: %zu vs %zu", hl->len, hr->len);
+    const uint64_t lid = hl->id, rid = hr->id;
+    const int32_t dtype = hl->dtype;
+    const size_t len = hl->len;
+    if (lid == rid) return fail(CB_ERR_INVALID_ARG, "each parent (id) must be unique");  // lazy_graph.rs:112-128
+    // README.md:96-122: retrieve(len, (lhs, rhs)) then add_op((lhs, rhs, &mut out), ..)
+    const cbm_buf parents[2] = {lhs, rhs};
+    cbm_buf ob = 0;
+    CB_TRY(retrieve(d, dtype, len, parents, 2, &ob));
+    const uint64_t out_id = d->handle(ob)->id;
+    Op o;
+    o.kind = OpKind::Binary;
+    o.dtype = dtype;
+    o.binop = op;
+    o.arg_ids = {lid, rid, out_id};
+    if (d->recording()) d->op_of_id[out_id] = d->ops.size();
+    int32_t rc = add_op(d, std::move(o));
+    if (rc != CB_OK) return rc;
+    *out = ob;
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_clear(cbm_device *d, cbm_buf b)
+{
+    CB_CHECK_ARG(d, "null device");
+    GET_HANDLE(h, d, b);
+    Entry e;
+    CB_TRY(storage_of(d, h, &e));
+    return cb_clear(d->raw, h->dtype, e.ptr, e.len);  // ClearBuf::clear is eager (src/devices/cuda/ops.rs:51-56)
+}
+
+extern "C" int32_t cbm_copy_slice(cbm_device *d, cbm_buf src, size_t src_off, cbm_buf dst, size_t dst_off, size_t n)
+{
+    CB_CHECK_ARG(d, "null device");
+    GET_HANDLE(hs, d, src);
+    GET_HANDLE(hd, d, dst);
+    if (hs->dtype != hd->dtype) return fail(CB_ERR_INVALID_ARG, "dtype mismatch");
+    Entry es, ed;
+    CB_TRY(storage_of(d, hs, &es));
+    CB_TRY(storage_of(d, hd, &ed));
+    if (src_off + n > es.len || dst_off + n > ed.len) return fail(CB_ERR_SHAPE, "slice out of range");
+    return cb_copy(d->raw, hs->dtype, ed.ptr, dst_off, es.ptr, src_off, n);
+}
+
+extern "C" int32_t cbm_clone_buf(cbm_device *d, cbm_buf src, cbm_buf *out)
+{
+    CB_CHECK_ARG(d && out, "null argument");
+    GET_HANDLE(hs, d, src);
+    Entry es;
+    CB_TRY(storage_of(d, hs, &es));
+    const int32_t dtype = hs->dtype;
+    cbm_buf nb = 0;
+    CB_TRY(cbm_buffer_new(d, dtype, es.len, &nb));  // CloneBuf (src/devices/cuda/cuda.rs:152-164)
+    CB_TRY(cb_copy(d->raw, dtype, d->handle(nb)->ptr, 0, es.ptr, 0, es.len));
+    *out = nb;
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_sum(cbm_device *d, cbm_buf b, void *host_out)
+{
+    CB_CHECK_ARG(d && host_out, "null argument");
+    GET_HANDLE(h, d, b);
+    Entry e;
+    CB_TRY(storage_of(d, h, &e));
+    return cb_sum_host(d->raw, h->dtype, e.ptr, e.len, host_out);
+}
+
+extern "C" int32_t cbm_mean(cbm_device *d, cbm_buf b, void *host_out)
+{
+    CB_CHECK_ARG(d && host_out, "null argument");
+    GET_HANDLE(h, d, b);
+    Entry e;
+    CB_TRY(storage_of(d, h, &e));
+    return cb_mean_host(d->raw, h->dtype, e.ptr, e.len, host_out);
+}
+
+// ===================================================================== Lazy
+extern "C" int32_t cbm_alloc_later(cbm_device *d)
+{
+    CB_CHECK_ARG(d, "null device");
+    return run_alloc_later(d);
+}
+
+extern "C" int32_t cbm_run(cbm_device *d)
+{
+    CB_CHECK_ARG(d, "null device");
+    if (!d->has(CBM_LAZY)) return CB_OK;  // Base: RunModule is a no-op
+    CB_TRY(run_alloc_later(d));           // lazy.rs:190-198: alloc, call every op, device.run()
+    if (!d->replay_enabled) return run_ops(d);
+    if (!d->replay_valid) {
+        // capture once, after every buffer exists; afterwards run() is a single cudaGraphLaunch
+        free_replay(d);
+        for (const Op &op : d->ops)  // fail before the capture starts if a buffer went away
+            for (uint64_t id : op.arg_ids)
+                if (op.kind != OpKind::NoOp && !d->resolve(id))
+                    return fail(CB_ERR_INVALID_LAZY_BUF, "InvalidLazyBuf: buffer id %llu is not alive", (unsigned long long)id);
+        CB_TRY(cb_graph_begin(d->raw));
+        int32_t rc = run_ops(d);
+        cb_graph *g = nullptr;
+        int32_t rc2 = cb_graph_end(d->raw, &g);
+        if (rc != CB_OK) {
+            if (g) cb_graph_destroy(g);
+            return rc;
+        }
+        CB_TRY(rc2);
+        d->replay = g;
+        d->replay_valid = true;
+    }
+    return cb_graph_launch(d->raw, d->replay);
+}
+
+extern "C" int32_t cbm_exec_now(cbm_device *d, size_t begin, size_t end)
+{
+    CB_CHECK_ARG(d, "null device");
+    if (!d->has(CBM_LAZY)) return CB_OK;
+    CB_TRY(run_alloc_later(d));
+    if (end > d->ops.size()) end = d->ops.size();
+    if (begin > end) return fail(CB_ERR_INVALID_ARG, "exec_now: begin %zu > end %zu", begin, end);
+    // call_range drains the operations it executes (lazy_graph.rs:92-104)
+    std::vector<Op> taken(std::make_move_iterator(d->ops.begin() + (ptrdiff_t)begin),
+                          std::make_move_iterator(d->ops.begin() + (ptrdiff_t)end));
+    d->ops.erase(d->ops.begin() + (ptrdiff_t)begin, d->ops.begin() + (ptrdiff_t)end);
+    d->op_of_id.clear();  // positions moved; fusing needs a freshly recorded sequence
+    d->invalidate_replay();
+    for (const Op &op : taken) CB_TRY(call_op(d, op));
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_exec_last_n(cbm_device *d, size_t n)
+{
+    CB_CHECK_ARG(d, "null device");
+    const size_t total = d->ops.size();
+    return cbm_exec_now(d, n > total ? 0 : total - n, total);  // features.rs:505-518
+}
+
+extern "C" int32_t cbm_ops_count(cbm_device *d, size_t *n)
+{
+    CB_CHECK_ARG(d && n, "null argument");
+    *n = d->ops.size();
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_set_lazy_enabled(cbm_device *d, int32_t enabled)
+{
+    CB_CHECK_ARG(d, "null device");
+    d->lazy_enabled = enabled != 0;
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_op_hint_src(cbm_device *d, size_t i, char *out, size_t cap)
+{
+    CB_CHECK_ARG(d && out && cap > 0, "bad argument");
+    if (i >= d->ops.size()) return fail(CB_ERR_INVALID_ARG, "op index %zu out of range (%zu ops)", i, d->ops.size());
+    const Op &op = d->ops[i];
+    std::string s;
+    if (op.unary_hint) s = expr_to_cl_source(op.dtype, op.hint.data(), (int32_t)op.hint.size(), "x", "y");
+    else if (op.fused) s = "UnaryFused";
+    if (s.size() + 1 > cap) return fail(CB_ERR_INVALID_ARG, "output buffer too small");
+    std::memcpy(out, s.c_str(), s.size() + 1);
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_set_graph_replay(cbm_device *d, int32_t enabled)
+{
+    CB_CHECK_ARG(d, "null device");
+    d->replay_enabled = enabled != 0;
+    if (!d->replay_enabled) free_replay(d);
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_replay_kernel_nodes(cbm_device *d, size_t *n)
+{
+    CB_CHECK_ARG(d && n, "null argument");
+    *n = 0;
+    if (d->replay && d->replay_valid) return cb_graph_node_count(d->replay, n);
+    return CB_OK;
+}
+
+// ===================================================================== Graph
+extern "C" int32_t cbm_cache_traces(cbm_device *d, int64_t *out, size_t cap, size_t *written)
+{
+    CB_CHECK_ARG(d, "null device");
+    if (!d->has(CBM_GRAPH)) return fail(CB_ERR_MISSING_CACHE_TRACES, "MissingCacheTraces: no Graph module");
+    return cb_flatten_traces(d->graph.cache_traces(), out, cap, written);
+}
+
+extern "C" int32_t cbm_optimize_mem_graph(cbm_device *d)
+{
+    CB_CHECK_ARG(d, "null device");
+    if (!d->has(CBM_GRAPH)) return fail(CB_ERR_MISSING_CACHE_TRACES, "MissingCacheTraces: no Graph module");
+    const std::vector<CacheTrace> traces = d->graph.cache_traces();
+    if (d->has(CBM_LAZY)) {
+        // Lazy::alloc_later_optimized (lazy/optimization.rs:4-44): allocate the head of each trace
+        // and register the same storage under every id of the trace
+        std::unordered_set<uint64_t> aliased;
+        std::vector<Deferred> pending;
+        pending.swap(d->alloc_later);
+        std::unordered_map<uint64_t, Deferred> by_id;
+        for (const Deferred &a : pending) by_id.emplace(a.id, a);
+        for (const CacheTrace &t : traces) {
+            auto head = d->idx_to_buf_id.find(t.cache_idx);
+            if (head == d->idx_to_buf_id.end()) return fail(CB_ERR_GRAPH_OPTIMIZATION, "GraphOptimization: trace head has no buffer");
+            auto def = by_id.find(head->second);
+            if (def == by_id.end()) continue;  // allocated earlier: nothing to share any more
+            const Deferred a = def->second;
+            if (!d->allocated_ids.count(a.id)) {
+                if (d->buffers.count(a.id)) return fail(CB_ERR_STATE, "IDs collided! Maybe pointing address already occupied this ID.");
+                uint64_t p = 0;
+                CB_TRY(alloc_zeroed(d, a.dtype, a.len, &p));
+                d->lazy_allocs.push_back(p);
+                d->allocated_ids.insert(a.id);
+                d->buffers[a.id] = Entry{p, a.len, a.dtype};
+            }
+            aliased.insert(a.id);
+            const Entry shared = d->buffers[a.id];
+            for (size_t use : t.use_cache_idxs) {
+                auto uid = d->idx_to_buf_id.find(use);
+                if (uid == d->idx_to_buf_id.end()) return fail(CB_ERR_GRAPH_OPTIMIZATION, "GraphOptimization: trace node has no buffer");
+                auto udef = by_id.find(uid->second);
+                if (udef == by_id.end()) continue;
+                if (udef->second.dtype != a.dtype || udef->second.len != a.len) continue;  // never alias across types
+                d->buffers[uid->second] = shared;
+                d->allocated_ids.insert(uid->second);
+                aliased.insert(uid->second);
+            }
+        }
+        for (const Deferred &a : pending)
+            if (!aliased.count(a.id)) d->alloc_later.push_back(a);  // not on a trace: allocated by run()
+        d->invalidate_replay();
+        return CB_OK;
+    }
+    // Cached::optimize_mem_graph (cached.rs:414-448): later iterations of the loop hand out the
+    // head's allocation for every cursor position of the trace
+    for (const CacheTrace &t : traces) {
+        auto hc = d->idx_to_cursor.find(t.cache_idx);
+        if (hc == d->idx_to_cursor.end()) return fail(CB_ERR_GRAPH_OPTIMIZATION, "GraphOptimization: trace head has no cursor");
+        auto head = d->cache.find(hc->second);
+        if (head == d->cache.end()) return fail(CB_ERR_GRAPH_OPTIMIZATION, "GraphOptimization: trace head is not cached");
+        for (size_t use : t.use_cache_idxs) {
+            auto uc = d->idx_to_cursor.find(use);
+            if (uc == d->idx_to_cursor.end()) continue;
+            auto slot = d->cache.find(uc->second);
+            if (slot == d->cache.end()) continue;
+            if (slot->second.dtype != head->second.dtype || slot->second.len != head->second.len) continue;
+            slot->second = head->second;  // the old allocation stays owned by live handles of this iteration
+        }
+    }
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_unary_fusing(cbm_device *d)
+{
+    CB_CHECK_ARG(d, "null device");
+    if (!d->has(CBM_GRAPH)) return fail(CB_ERR_MISSING_CACHE_TRACES, "MissingCacheTraces: no Graph module");
+    if (!d->has(CBM_LAZY)) return fail(CB_ERR_UNSUPPORTED, "UnaryFusingUnsupported: only Lazy records operations");
+    // Lazy::fuse_unary_ops (lazy/optimization.rs:46-95) + UnaryFusing::fuse_unary_ops (devices/fusing.rs:41-92)
+    for (const CacheTrace &t : d->graph.cache_traces()) {
+        std::vector<size_t> idxs{t.cache_idx};
+        idxs.insert(idxs.end(), t.use_cache_idxs.begin(), t.use_cache_idxs.end());
+        // node index -> id of the retrieved buffer -> the op that writes it
+        std::vector<long> op_idx;
+        for (size_t idx : idxs) {
+            long oi = -1;
+            auto id = d->idx_to_buf_id.find(idx);
+            if (id != d->idx_to_buf_id.end()) {
+                auto o = d->op_of_id.find(id->second);
+                if (o != d->op_of_id.end() && o->second < d->ops.size()) oi = (long)o->second;
+            }
+            op_idx.push_back(oi);
+        }
+        size_t i = 0;
+        while (i < op_idx.size()) {
+            auto fusable = [&](size_t k, int32_t dtype, size_t prev_k) {
+                if (op_idx[k] < 0) return false;
+                const Op &o = d->ops[(size_t)op_idx[k]];
+                if (!(o.kind == OpKind::Apply && o.unary_hint) || o.dtype != dtype) return false;
+                // the op must consume what the previous op of the run produced
+                return k == prev_k || o.arg_ids[1] == d->ops[(size_t)op_idx[prev_k]].arg_ids[0];
+            };
+            if (op_idx[i] < 0 || !(d->ops[(size_t)op_idx[i]].kind == OpKind::Apply && d->ops[(size_t)op_idx[i]].unary_hint)) {
+                i++;
+                continue;
+            }
+            const int32_t dtype = d->ops[(size_t)op_idx[i]].dtype;
+            size_t j = i + 1;
+            while (j < op_idx.size() && fusable(j, dtype, j - 1)) j++;
+            if (j - i >= 2) {
+                Op &first = d->ops[(size_t)op_idx[i]];
+                const Op &last = d->ops[(size_t)op_idx[j - 1]];
+                // out = the last op's output, in = the first op's input; they must differ (fusing.rs:60-67)
+                if (last.arg_ids[0] == first.arg_ids[1]) return fail(CB_ERR_STATE, "fused chain would read and write the same buffer id");
+                std::vector<const cb_node *> progs;
+                std::vector<int32_t> counts;
+                for (size_t k = i; k < j; k++) {
+                    const Op &o = d->ops[(size_t)op_idx[k]];
+                    progs.push_back(o.hint.data());
+                    counts.push_back((int32_t)o.hint.size());
+                }
+                cb_expr *fused = nullptr;
+                CB_TRY(cb_expr_compile(d->raw, dtype, CB_KERNEL_APPLY, progs.data(), counts.data(), (int32_t)progs.size(), &fused));
+                const uint64_t out_id = last.arg_ids[0], in_id = first.arg_ids[1];
+                for (size_t k = i + 1; k < j; k++) d->ops[(size_t)op_idx[k]] = Op();  // Operation::no_op()
+                first.expr = fused;
+                first.arg_ids = {out_id, in_id};
+                first.unary_hint = false;
+                first.hint.clear();
+                first.fused = true;  // OpHint::UnaryFused
+            }
+            i = j;
+        }
+    }
+    d->invalidate_replay();
+    return CB_OK;
+}
+
+// ===================================================================== Cached: cursor
+extern "C" int32_t cbm_cursor(cbm_device *d, uint64_t *cursor)
+{
+    CB_CHECK_ARG(d && cursor, "null argument");
+    *cursor = d->cursor;
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_set_cursor(cbm_device *d, uint64_t cursor)
+{
+    CB_CHECK_ARG(d, "null device");
+    d->cursor = cursor;
+    return CB_OK;
+}
+
+// ===================================================================== Autograd
+extern "C" int32_t cbm_grad(cbm_device *d, cbm_buf b, cbm_buf *grad)
+{
+    CB_CHECK_ARG(d && grad, "null argument");
+    if (!d->has(CBM_AUTOGRAD)) return fail(CB_ERR_STATE, "Autograd<> is not available.");  // impl_autograd.rs:9
+    GET_HANDLE(h, d, b);
+    const uint64_t id = h->id;
+    Entry *g = nullptr;
+    CB_TRY(grad_entry(d, id, h->len, h->dtype, &g));
+    auto it = d->grad_handle.find(id);
+    if (it != d->grad_handle.end() && d->handle(it->second)) {
+        *grad = it->second;
+        return CB_OK;
+    }
+    Handle gh;
+    gh.id = g->ptr;
+    gh.ptr = g->ptr;
+    gh.len = g->len;
+    gh.dtype = g->dtype;
+    gh.owned = false;  // owned by the gradient pool
+    d->buffers[gh.id] = *g;
+    *grad = d->new_handle(gh);
+    d->grad_handle[id] = *grad;
+    return CB_OK;
+}
+
+static int32_t backward_impl(cbm_device *d, cbm_buf out, const void *seed, size_t seed_len)
+{
+    if (!d->has(CBM_AUTOGRAD)) return CB_OK;  // "should never be None" — without a tape nothing happens
+    GET_HANDLE(ho, d, out);
+    Entry *og = nullptr;
+    CB_TRY(grad_entry(d, ho->id, ho->len, ho->dtype, &og));
+    if (seed) {
+        if (seed_len != og->len) return fail(CB_ERR_SHAPE, "seed of %zu elements for a buffer of %zu", seed_len, og->len);
+        CB_TRY(cb_h2d(d->raw, og->ptr, seed, seed_len * dtype_size(og->dtype)));  // tape.rs:53-64
+    } else {
+        CB_TRY(cb_fill(d->raw, og->dtype, og->ptr, og->len, 1.0, 1));  // vec![T::one(); len], on the device
+    }
+    // device.eagerly(|| tape.backward(..)): grad ops run now even under Lazy (tape.rs:78-82)
+    const bool lazy_was_enabled = d->lazy_enabled;
+    const bool is_lazy_enabled = d->recording();
+    d->lazy_enabled = false;
+    int32_t rc = CB_OK;
+    for (auto it = d->tape.rbegin(); it != d->tape.rend() && rc == CB_OK; ++it) {
+        const GradOp &g = *it;
+        const Entry *buf = d->resolve(g.buf_id);
+        const Entry *o = d->resolve(g.out_id);
+        if (!buf || !o) {
+            rc = fail(CB_ERR_INVALID_LAZY_BUF, "InvalidLazyBuf: a buffer of a grad function is not alive");
+            break;
+        }
+        auto rg = d->requires_grad.find(g.buf_id);
+        if (rg == d->requires_grad.end() || !rg->second) continue;  // if !buf.requires_grad() { return Ok(()) }
+        Entry *bg = nullptr, *outg = nullptr;
+        rc = grad_entry(d, g.buf_id, buf->len, buf->dtype, &bg);
+        if (rc == CB_OK) rc = grad_entry(d, g.out_id, o->len, o->dtype, &outg);
+        if (rc == CB_OK) rc = cb_unary_grad(d->raw, g.grad_expr, buf->ptr, bg->ptr, outg->ptr, buf->len);
+    }
+    d->lazy_enabled = lazy_was_enabled;
+    if (!is_lazy_enabled) d->tape.clear();  // tape.rs:48-50
+    return rc;
+}
+
+extern "C" int32_t cbm_backward(cbm_device *d, cbm_buf out)
+{
+    CB_CHECK_ARG(d, "null device");
+    return backward_impl(d, out, nullptr, 0);
+}
+
+extern "C" int32_t cbm_backward_with(cbm_device *d, cbm_buf out, const void *seed, size_t len)
+{
+    CB_CHECK_ARG(d && seed, "null argument");
+    return backward_impl(d, out, seed, len);
+}
+
+extern "C" int32_t cbm_zero_grad(cbm_device *d)
+{
+    CB_CHECK_ARG(d, "null device");
+    for (auto &kv : d->grads) {
+        auto rg = d->requires_grad.find(kv.first);
+        if (rg != d->requires_grad.end() && !rg->second) continue;  // gradients.rs:33-38
+        CB_TRY(cb_clear(d->raw, kv.second.dtype, kv.second.ptr, kv.second.len));
+    }
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_set_grad_enabled(cbm_device *d, int32_t enabled)
+{
+    CB_CHECK_ARG(d, "null device");
+    d->grad_enabled = enabled != 0;
+    return CB_OK;
+}

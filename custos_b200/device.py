@@ -1,0 +1,305 @@
+"""Python mirror of the reference's operator interface over the module-layer C ABI (cbm_*).
+
+    dev = CUDA("Graph", "Lazy", "Base")            # CUDA::<Graph<Lazy<Base>>>::new(0)
+    buf = dev.buffer([1., 2., 3., 4., 5.])
+    out = dev.apply_fn(buf, lambda x: x.sin())     # ApplyFunction::apply_fn
+    dev.optimize_mem_graph(); dev.unary_fusing(); dev.run()
+    out.replace().read()
+
+Names, argument meaning and error behaviour follow the reference (src/unary.rs,
+src/op_traits.rs, src/features.rs, src/buffer.rs) so that the parity tests read like the
+reference's own tests.  All work happens in libcustos_b200.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Iterable, Sequence
+
+import numpy as np
+
+from . import _native as N
+from .expr import NP_DTYPE, dtype_code, flatten
+from .raw import RawDevice
+
+MODULE_BITS = {"Base": N.CBM_BASE, "Cached": N.CBM_CACHED, "Lazy": N.CBM_LAZY, "Graph": N.CBM_GRAPH,
+               "Autograd": N.CBM_AUTOGRAD}
+
+
+class Buffer:
+    """`Buffer<'a, T, CUDA<Mods>>` (src/buffer.rs:43-49): a handle, not the data."""
+
+    def __init__(self, device: "CUDA", handle: int, dtype: int):
+        self.device, self.handle, self.dtype = device, handle, dtype
+
+    def __len__(self) -> int:
+        n = C.c_size_t()
+        N.call("cbm_buffer_len", self.device.h, self.handle, C.byref(n))
+        return n.value
+
+    len = __len__
+
+    def id(self) -> int:
+        v = C.c_uint64()
+        N.call("cbm_buffer_id", self.device.h, self.handle, C.byref(v))
+        return v.value
+
+    def ptr(self) -> int:
+        """Device address after `replace()`; 0 while a lazy buffer has no storage."""
+        v = C.c_uint64()
+        N.call("cbm_buffer_ptr", self.device.h, self.handle, C.byref(v))
+        return v.value
+
+    def replace(self) -> "Buffer":
+        """Buffer::replace (src/modules/lazy.rs:430-455): reads always resolve by id."""
+        return self
+
+    def read(self) -> np.ndarray:
+        out = np.empty(len(self), NP_DTYPE[self.dtype])
+        N.call("cbm_buffer_read", self.device.h, self.handle, out.ctypes.data_as(C.c_void_p), out.size)
+        return out
+
+    read_to_vec = read
+
+    def write(self, data) -> None:
+        arr = np.ascontiguousarray(data, NP_DTYPE[self.dtype])
+        N.call("cbm_buffer_write", self.device.h, self.handle, arr.ctypes.data_as(C.c_void_p), arr.size)
+
+    def clear(self) -> None:
+        N.call("cbm_clear", self.device.h, self.handle)
+
+    def require_grad(self) -> "Buffer":
+        N.call("cbm_buffer_require_grad", self.device.h, self.handle)
+        return self
+
+    def requires_grad(self) -> bool:
+        v = C.c_int32()
+        N.call("cbm_buffer_requires_grad", self.device.h, self.handle, C.byref(v))
+        return bool(v.value)
+
+    def checkpoint(self) -> "Buffer":
+        N.call("cbm_buffer_checkpoint", self.device.h, self.handle)
+        return self
+
+    def grad(self) -> "Buffer":
+        g = C.c_uint64()
+        N.call("cbm_grad", self.device.h, self.handle, C.byref(g))
+        return Buffer(self.device, g.value, self.dtype)
+
+    def backward(self) -> None:
+        N.call("cbm_backward", self.device.h, self.handle)
+
+    def backward_with(self, seed) -> None:
+        arr = np.ascontiguousarray(seed, NP_DTYPE[self.dtype])
+        N.call("cbm_backward_with", self.device.h, self.handle, arr.ctypes.data_as(C.c_void_p), arr.size)
+
+    def empty_like(self) -> "Buffer":
+        return self.device.new_buffer(self.dtype, len(self))
+
+    def clone(self) -> "Buffer":
+        out = C.c_uint64()
+        N.call("cbm_clone_buf", self.device.h, self.handle, C.byref(out))
+        return Buffer(self.device, out.value, self.dtype)
+
+    def drop(self) -> None:
+        """End of the Rust scope of the buffer."""
+        N.call("cbm_buffer_drop", self.device.h, self.handle)
+
+
+class CUDA:
+    """`CUDA<Mods>`; the module stack is given outermost first, e.g. CUDA("Graph", "Lazy", "Base")."""
+
+    def __init__(self, *modules: str, ordinal: int = 0, dtype=np.float32):
+        bits = 0
+        for m in modules:
+            bits |= MODULE_BITS[m]
+        self.modules = modules
+        self.h = C.c_void_p()
+        N.call("cbm_device_create", ordinal, bits, dtype_code(dtype), C.byref(self.h))
+        raw = C.c_void_p()
+        N.call("cbm_device_raw", self.h, C.byref(raw))
+        self.raw = RawDevice.from_handle(raw)
+
+    def close(self):
+        if self.h:
+            N.call("cbm_device_destroy", self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ------------------------------------------------------------ buffers
+    def buffer(self, data, dtype=None) -> Buffer:
+        """device.buffer([..]) / Buffer::from((&device, [..]))"""
+        if dtype is None:
+            if isinstance(data, np.ndarray):
+                dtype = data.dtype
+            else:  # Python literals: f32 for floats (the modules' default T), i32 for integers (Rust's default)
+                dtype = np.float32 if np.asarray(data).dtype.kind == "f" else np.int32
+        dt = dtype_code(dtype)
+        arr = np.ascontiguousarray(data, NP_DTYPE[dt])
+        out = C.c_uint64()
+        N.call("cbm_buffer_from_host", self.h, dt, arr.ctypes.data_as(C.c_void_p), arr.size, C.byref(out))
+        return Buffer(self, out.value, dt)
+
+    def new_buffer(self, dtype, length: int) -> Buffer:
+        """Buffer::<T, _>::new(&device, len): zero initialised."""
+        dt = dtype_code(dtype)
+        out = C.c_uint64()
+        N.call("cbm_buffer_new", self.h, dt, length, C.byref(out))
+        return Buffer(self, out.value, dt)
+
+    def retrieve(self, length: int, parents: Sequence[Buffer] = (), dtype=np.float32) -> Buffer:
+        """Retriever::retrieve (src/devices.rs:172-186)"""
+        dt = dtype_code(dtype)
+        arr = (C.c_uint64 * max(len(parents), 1))(*[p.handle for p in parents])
+        out = C.c_uint64()
+        N.call("cbm_retrieve", self.h, dt, length, arr, len(parents), C.byref(out))
+        return Buffer(self, out.value, dt)
+
+    # ------------------------------------------------------------ operator traits
+    def apply_fn(self, buf: Buffer, f: Callable) -> Buffer:
+        """ApplyFunction::apply_fn (src/unary.rs:7-28)"""
+        nodes, n = flatten(f, buf.dtype)
+        out = C.c_uint64()
+        N.call("cbm_apply_fn", self.h, buf.handle, nodes, n, C.byref(out))
+        return Buffer(self, out.value, buf.dtype)
+
+    def add_unary_grad(self, lhs: Buffer, lhs_grad: Buffer, out: Buffer, lhs_grad_fn: Callable) -> None:
+        """UnaryGrad::add_unary_grad (src/unary.rs:31-58): lhs_grad += out * lhs_grad_fn(lhs)"""
+        nodes, n = flatten(lhs_grad_fn, lhs.dtype)
+        N.call("cbm_add_unary_grad", self.h, lhs.handle, lhs_grad.handle, out.handle, nodes, n)
+
+    def unary_ew(self, buf: Buffer, forward_fn: Callable, grad_fn: Callable) -> Buffer:
+        """UnaryElementWiseMayGrad::unary_ew (src/unary.rs:62-132)"""
+        fwd, nf = flatten(forward_fn, buf.dtype)
+        grd, ng = flatten(grad_fn, buf.dtype)
+        out = C.c_uint64()
+        N.call("cbm_unary_ew", self.h, buf.handle, fwd, nf, grd, ng, C.byref(out))
+        return Buffer(self, out.value, buf.dtype)
+
+    def _binary(self, op: int, lhs: Buffer, rhs: Buffer) -> Buffer:
+        out = C.c_uint64()
+        N.call("cbm_binary", self.h, op, lhs.handle, rhs.handle, C.byref(out))
+        return Buffer(self, out.value, lhs.dtype)
+
+    def add(self, lhs: Buffer, rhs: Buffer) -> Buffer:
+        """AddEw::add (src/lib.rs:293-301)"""
+        return self._binary(N.BIN_ADD, lhs, rhs)
+
+    def mul(self, lhs: Buffer, rhs: Buffer) -> Buffer:
+        """MulBuf::mul (README.md:96-122)"""
+        return self._binary(N.BIN_MUL, lhs, rhs)
+
+    def sub(self, lhs: Buffer, rhs: Buffer) -> Buffer:
+        return self._binary(N.BIN_SUB, lhs, rhs)
+
+    def div(self, lhs: Buffer, rhs: Buffer) -> Buffer:
+        return self._binary(N.BIN_DIV, lhs, rhs)
+
+    def clear(self, buf: Buffer) -> None:
+        buf.clear()
+
+    def copy_slice_to(self, source: Buffer, source_range: range, dest: Buffer, dest_range: range) -> None:
+        """CopySlice::copy_slice_to (src/op_traits.rs:34-60)"""
+        assert len(source_range) == len(dest_range)
+        N.call("cbm_copy_slice", self.h, source.handle, source_range.start, dest.handle, dest_range.start,
+               len(source_range))
+
+    def copy_slice_all(self, source: Buffer, dest: Buffer, ranges: Iterable) -> None:
+        for sr, dr in ranges:
+            self.copy_slice_to(source, sr, dest, dr)
+
+    def write_buf(self, dst: Buffer, src: Buffer) -> None:
+        """WriteBuf::write_buf"""
+        N.call("cbm_copy_slice", self.h, src.handle, 0, dst.handle, 0, len(src))
+
+    def sum(self, buf: Buffer):
+        out = np.zeros(1, RawDevice.acc_dtype(buf.dtype))
+        N.call("cbm_sum", self.h, buf.handle, out.ctypes.data_as(C.c_void_p))
+        return out[0]
+
+    def mean(self, buf: Buffer):
+        out = np.zeros(1, RawDevice.acc_dtype(buf.dtype))
+        N.call("cbm_mean", self.h, buf.handle, out.ctypes.data_as(C.c_void_p))
+        return out[0]
+
+    # ------------------------------------------------------------ Lazy
+    def run(self) -> None:
+        N.call("cbm_run", self.h)
+
+    def exec_now(self, begin: int = 0, end: int | None = None) -> None:
+        N.call("cbm_exec_now", self.h, begin, (1 << 64) - 1 if end is None else end)
+
+    def exec_last_n(self, n: int) -> None:
+        N.call("cbm_exec_last_n", self.h, n)
+
+    def ops_count(self) -> int:
+        v = C.c_size_t()
+        N.call("cbm_ops_count", self.h, C.byref(v))
+        return v.value
+
+    def alloc_later(self) -> None:
+        N.call("cbm_alloc_later", self.h)
+
+    def op_hint_src(self, i: int) -> str:
+        buf = C.create_string_buffer(1 << 14)
+        N.call("cbm_op_hint_src", self.h, i, buf, len(buf))
+        return buf.value.decode()
+
+    def set_graph_replay(self, enabled: bool) -> None:
+        N.call("cbm_set_graph_replay", self.h, 1 if enabled else 0)
+
+    def replay_kernel_nodes(self) -> int:
+        v = C.c_size_t()
+        N.call("cbm_replay_kernel_nodes", self.h, C.byref(v))
+        return v.value
+
+    # ------------------------------------------------------------ Graph
+    def optimize_mem_graph(self) -> None:
+        N.call("cbm_optimize_mem_graph", self.h)
+
+    def unary_fusing(self) -> None:
+        N.call("cbm_unary_fusing", self.h)
+
+    def cache_traces(self):
+        cap = 1 << 16
+        buf = (C.c_int64 * cap)()
+        w = C.c_size_t()
+        N.call("cbm_cache_traces", self.h, buf, cap, C.byref(w))
+        flat, out, i = [int(buf[k]) for k in range(w.value)], [], 0
+        while i < len(flat):
+            out.append((flat[i], flat[i + 2:i + 2 + flat[i + 1]]))
+            i += 2 + flat[i + 1]
+        return out
+
+    # ------------------------------------------------------------ Cached
+    def cursor(self) -> int:
+        v = C.c_uint64()
+        N.call("cbm_cursor", self.h, C.byref(v))
+        return v.value
+
+    def set_cursor(self, cursor: int) -> None:
+        N.call("cbm_set_cursor", self.h, cursor)
+
+    def range(self, *args):
+        """device.range(..) (src/range.rs:35-48): every iteration starts at the same cursor."""
+        start = self.cursor()
+        for i in range(*args):
+            self.set_cursor(start)
+            yield i
+
+    # ------------------------------------------------------------ Autograd
+    def zero_grad(self) -> None:
+        N.call("cbm_zero_grad", self.h)
+
+    def disable_grad(self) -> None:
+        N.call("cbm_set_grad_enabled", self.h, 0)
+
+    def enable_grad(self) -> None:
+        N.call("cbm_set_grad_enabled", self.h, 1)
+
+    def sync(self) -> None:
+        self.raw.sync()
