@@ -362,6 +362,7 @@ cudaError_t launch_sum_t(const LaunchCtx &ctx, const void *in, size_t n, int blo
 // ------------------------------------------------------------------ host launchers
 cudaError_t launch_binary(const LaunchCtx &ctx, int dtype, int op, const void *lhs, const void *rhs, void *out, size_t n)
 {
+    (void)cudaGetLastError();  // a stale error of an earlier, unchecked call must not be blamed on this launch
     switch (dtype) {
     case CB_F32: return launch_binary_op<float>(ctx, op, lhs, rhs, out, n);
     case CB_F64: return launch_binary_op<double>(ctx, op, lhs, rhs, out, n);
@@ -376,6 +377,7 @@ cudaError_t launch_binary(const LaunchCtx &ctx, int dtype, int op, const void *l
 
 cudaError_t launch_fill(const LaunchCtx &ctx, void *out, size_t n, int elem_bytes, uint64_t pattern)
 {
+    (void)cudaGetLastError();  // a stale error of an earlier, unchecked call must not be blamed on this launch
     // replicate the element pattern over 16 bytes
     uint64_t p64 = pattern;
     if (elem_bytes == 1) p64 = (pattern & 0xffu) * 0x0101010101010101ull;
@@ -417,6 +419,7 @@ int launch_fill_count(const void *out, size_t n, int elem_bytes)
 
 cudaError_t launch_copy(const LaunchCtx &ctx, void *dst, const void *src, size_t bytes)
 {
+    (void)cudaGetLastError();  // a stale error of an earlier, unchecked call must not be blamed on this launch
     if (!bytes) return cudaSuccess;
     if (aligned16(dst) && aligned16(src)) {
         const size_t units = bytes / 16;
@@ -468,6 +471,7 @@ void sum_plan(int dtype, size_t n, int *blocks, size_t *chunk, int *threads, int
 
 cudaError_t launch_sum(const LaunchCtx &ctx, int dtype, const void *in, size_t n, void *partials, void *out, size_t divisor)
 {
+    (void)cudaGetLastError();  // a stale error of an earlier, unchecked call must not be blamed on this launch
     int blocks, threads, vec, threads2;
     size_t chunk;
     sum_plan(dtype, n, &blocks, &chunk, &threads, &vec, &threads2);
@@ -485,6 +489,7 @@ cudaError_t launch_sum(const LaunchCtx &ctx, int dtype, const void *in, size_t n
 
 cudaError_t launch_fold_ranks(const LaunchCtx &ctx, int dtype, const void *gathered, int n_ranks, void *out, size_t divisor)
 {
+    (void)cudaGetLastError();  // a stale error of an earlier, unchecked call must not be blamed on this launch
     switch (dtype) {
     case CB_F32: case CB_F16:
         fold_ranks_kernel<float><<<1, 32, 0, ctx.stream>>>((const float *)gathered, n_ranks, (float *)out, divisor);

@@ -111,6 +111,7 @@ struct cbm_device {
     // Cursor (features.rs:68-111): shared by Cached / Lazy, read by Graph
     uint64_t cursor = 0;
     std::unordered_map<uint64_t, CacheSlot> cache;  // Cached: cursor -> allocation
+    std::vector<uint64_t> cache_orphans;            // allocations replaced by aliasing, freed with the device
 
     // Lazy
     bool lazy_enabled = true;
@@ -365,7 +366,14 @@ extern "C" int32_t cbm_device_destroy(cbm_device *d)
     for (auto &kv : d->handles)
         if (kv.second.owned && kv.second.ptr) cb_free(d->raw, kv.second.ptr);
     for (uint64_t p : d->lazy_allocs) cb_free(d->raw, p);
-    for (auto &kv : d->cache) cb_free(d->raw, kv.second.ptr);
+    {
+        // after optimize_mem_graph several cursor positions share one allocation: free each once
+        std::unordered_set<uint64_t> freed;
+        for (auto &kv : d->cache)
+            if (freed.insert(kv.second.ptr).second) cb_free(d->raw, kv.second.ptr);
+        for (uint64_t p : d->cache_orphans)
+            if (freed.insert(p).second) cb_free(d->raw, p);
+    }
     for (auto &kv : d->grads) cb_free(d->raw, kv.second.ptr);
     cb_device_destroy(d->raw);
     delete d;
@@ -848,7 +856,8 @@ extern "C" int32_t cbm_optimize_mem_graph(cbm_device *d)
             auto slot = d->cache.find(uc->second);
             if (slot == d->cache.end()) continue;
             if (slot->second.dtype != head->second.dtype || slot->second.len != head->second.len) continue;
-            slot->second = head->second;  // the old allocation stays owned by live handles of this iteration
+            if (slot->second.ptr != head->second.ptr) d->cache_orphans.push_back(slot->second.ptr);  // still used by this iteration's handles
+            slot->second = head->second;
         }
     }
     return CB_OK;

@@ -1,0 +1,5 @@
+#!/bin/bash
+# GPU test suite only (run through gpurun); log goes to gpurun_out/pytest_gpu.log
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q "$@" > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -40 gpurun_out/pytest_gpu.log
