@@ -20,7 +20,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -58,53 +57,58 @@ def ncu_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock, power and throttle reasons polled through NVML (about 1 kHz) from a helper thread,
+    so that even a 20 ms timed region gets its own samples; `nvidia-smi` exposes the same counters
+    (B200_PROFILING.md recipe) but cannot be sampled faster than every ~50 ms."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, gpu_index: int):
-        self.rows, self.proc = [], None
+        self.samples, self.ok, self._stop = [], False, threading.Event()
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if visible:
+                try:
+                    gpu_index = int(visible.split(",")[gpu_index])
+                except ValueError:
+                    pass
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def wait_first(self, timeout: float):
-        t_end = time.time() + timeout
-        while self.proc and not self.rows and time.time() < t_end:
-            time.sleep(0.01)
-
-    def stop(self, t0: float, t1: float):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
-        sm, mx, reasons, power = [], None, set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = [r for (t, r) in self.rows if t0 + 0.1 <= t <= t1] or [r for (_, r) in self.rows]
-        for r in rows:
-            f = [c.strip() for c in r.split(",")]
+    def _poll(self):
+        nv, h = self.nv, self.h
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
             try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
-                power.append(float(f[2]))
-                for name, v in zip(names, f[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "power_w_max": max(power) if power else None, "samples": len(sm),
-                "how": "nvidia-smi -lms 50 while the timed kernel runs back to back (0.4 s before, the timed steps, 0.4 s after)"}
+                self.samples.append((time.time(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                     nv.nvmlDeviceGetPowerUsage(h) / 1000.0, int(reasons_fn(h))))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.0005)
+
+    def window(self, t0: float, t1: float, how: str):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {getattr(self, 'err', '')}"]}
+        rows = [r for r in self.samples if t0 <= r[0] <= t1]
+        if not rows:  # region shorter than one poll: take the nearest samples
+            rows = sorted(self.samples, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))[:3]
+        mask = 0
+        for r in rows:
+            mask |= r[3]
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": self.max_sm,
+                "reasons": sorted(name for bit, name in self.REASONS.items() if mask & bit),
+                "power_w_max": max(r[2] for r in rows), "samples": len(rows), "how": how}
+
+    def stop(self):
+        self._stop.set()
 
 
 def make_input(n: int, seed: int = 4) -> np.ndarray:
@@ -209,39 +213,46 @@ def run_ours(args):
     dev.sync()
 
     # ---------------------------------------------------------------- device-resident timing
-    def spin(seconds: float):
-        """untimed steps of the same kernel: keeps the GPU under the same load around the timed
-        region so that the nvidia-smi samples (50 ms period) describe it"""
-        t_end = time.time() + seconds
-        while time.time() < t_end:
-            for _ in range(20):
-                dev.apply(chain, d_in, d_out, n)
-            dev.sync()
-
     sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
         dev.apply(chain, d_in, d_out, n)
     dev.sync()
-    sampler.wait_first(2.0)
-    t_load0 = time.time()
-    spin(0.4)
     barrier()
     launches0 = dev.launches
     ev0, ev1 = dev.event(), dev.event()
+    t0 = time.time()
     ev0.record()
     for _ in range(args.steps):
         dev.apply(chain, d_in, d_out, n)
     ev1.record()
     ev1.sync()
     dev.sync()
+    t1 = time.time()
     launches = dev.launches - launches0
     barrier()
-    spin(0.4)
-    t_load1 = time.time()
     ms_total = max_over_ranks(ev0.elapsed_ms(ev1))
-    clocks = sampler.stop(t_load0, t_load1)
+    clocks = sampler.window(t0, t1, "NVML polled at ~1 kHz during the timed steps")
     ms_per_step = ms_total / args.steps
     value = world * n * BYTES_PER_ELEM / (ms_per_step * 1e-3) / 1e9
+
+    # the same kernel back to back for ~1 s: what a long-running job sees once the 1 kW power cap
+    # has pulled the SM clock down (reported beside the headline, never instead of it)
+    sus_steps = max(args.steps, int(1.0 / (ms_per_step * 1e-3)))
+    for _ in range(sus_steps // 2):
+        dev.apply(chain, d_in, d_out, n)
+    e0, e1 = dev.event(), dev.event()
+    ts0 = time.time()
+    e0.record()
+    for _ in range(sus_steps):
+        dev.apply(chain, d_in, d_out, n)
+    e1.record()
+    e1.sync()
+    ts1 = time.time()
+    sus_ms = max_over_ranks(e0.elapsed_ms(e1)) / sus_steps
+    sustained = {"value": world * n * BYTES_PER_ELEM / (sus_ms * 1e-3) / 1e9, "unit": "GB/s", "steps": sus_steps,
+                 "ms_per_step": sus_ms,
+                 "clocks": sampler.window(ts0, ts1, "NVML during the sustained loop (after 0.5 s of the same load)")}
+    sampler.stop()
 
     # ---------------------------------------------------------------- end to end (host buffers)
     e2e_steps = max(3, min(args.steps, 10))
@@ -289,6 +300,7 @@ def run_ours(args):
                 "ms_per_step": e2e_ms, "steps": e2e_steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "sustained": sustained,
     }
     if rank == 0 and world == 1:
         out["cpu_baseline"] = cpu_baseline_single(1 << 25)

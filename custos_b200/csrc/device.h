@@ -25,6 +25,8 @@ struct cb_expr {
     CUfunction fn_scalar = nullptr;
     int threads = 256;
     int unroll = 4;       // 16-byte units per thread per tile of the vector kernel
+    int resident_vec = 0;     // blocks of the vector / scalar kernel one SM holds (occupancy query):
+    int resident_scalar = 0;  // the persistent grid is exactly one wave of them
     size_t cubin_bytes = 0;
 };
 
@@ -43,6 +45,9 @@ struct Tunables {
     int unroll = 4;
     int min_blocks = 4;
     int blocks_per_sm = 8;
+    int waves = 16;  // CB_WAVES: grid cap = SMs x resident blocks x waves; >1 lets the hardware rebalance
+                     // SMs that run slower (a single static wave left ~10% on the table, profiles/r1_tuning.md)
+    int pair = 1;  // CB_PAIR: f32 chains evaluate two elements per thread on the packed f32x2 pipe
     std::string ld_mod = ".cs";
     std::string st_mod = ".cs";
     std::string dump_dir;  // CB_DUMP_DIR: write generated sources and cubins here
@@ -58,6 +63,7 @@ struct DriverApi {
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                              CUstream, void **, void **) = nullptr;
     CUresult (*GetErrorString)(CUresult, const char **) = nullptr;
+    CUresult (*OccupancyMaxActiveBlocks)(int *, CUfunction, int, size_t) = nullptr;
     bool loaded = false;
 };
 
@@ -96,7 +102,7 @@ struct cb_device {
     void *sum_scalar = nullptr;    // 8 bytes device
     void *sum_host = nullptr;      // 8 bytes pinned
 
-    cb::LaunchCtx ctx() const { return cb::LaunchCtx{stream, sm_count * cb::tunables().blocks_per_sm}; }
+    cb::LaunchCtx ctx() const { return cb::LaunchCtx{stream, sm_count * cb::tunables().blocks_per_sm * cb::tunables().waves}; }
     int32_t cuda_fail(cudaError_t e, const char *what) const;
     int32_t drv_fail(CUresult r, const char *what) const;
     int32_t use() const;  // cudaSetDevice

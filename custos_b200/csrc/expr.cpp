@@ -290,7 +290,33 @@ std::string expr_cuda_function(int32_t dtype, const cb_node *const *progs, const
         }
         s += "        x = t" + std::to_string(n - 1) + ";\n    }\n";
     }
-    s += "    return x;\n}\n}  // namespace CB_NS\n";
+    s += "    return x;\n}\n";
+    if (dtype == CB_F32) {
+        // the same programs on two elements at a time (one f32x2 register pair, see skeleton.cuh)
+        s += "#if CB_PAIR\n__device__ __forceinline__ cb_f2 cb_fn2(cb_f2 x, cb_f2 y, bool &redo)\n{\n";
+        for (int32_t k = 0; k < n_progs; k++) {
+            const cb_node *nd = progs[k];
+            const int32_t n = n_nodes[k];
+            s += "    { // op " + std::to_string(k) + "\n";
+            for (int32_t i = 0; i < n; i++) {
+                const cb_node &c = nd[i];
+                std::string rhs;
+                if (c.op == CB_OP_X) rhs = "x";
+                else if (c.op == CB_OP_Y) rhs = "y";
+                else if (c.op == CB_OP_CONST) rhs = "cb2_splat(" + cuda_literal(dtype, c) + ")";
+                else if (op_is_binary(c.op))
+                    rhs = "cb2_" + std::string(cuda_fn(c.op) + 3) + "(t" + std::to_string(c.a) + ", t" + std::to_string(c.b) + ")";
+                else if (c.op == CB_OP_SIN || c.op == CB_OP_COS)  // fast path only; `redo` asks for the scalar forms
+                    rhs = "cb2_" + std::string(cuda_fn(c.op) + 3) + "(t" + std::to_string(c.a) + ", redo)";
+                else
+                    rhs = "cb2_" + std::string(cuda_fn(c.op) + 3) + "(t" + std::to_string(c.a) + ")";
+                s += "        const cb_f2 t" + std::to_string(i) + " = " + rhs + ";\n";
+            }
+            s += "        x = t" + std::to_string(n - 1) + ";\n    }\n";
+        }
+        s += "    return x;\n}\n#endif\n";
+    }
+    s += "}  // namespace CB_NS\n";
     return s;
 }
 
