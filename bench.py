@@ -100,6 +100,8 @@ class ClockSampler:
         rows = [r for r in self.samples if t0 <= r[0] <= t1]
         if not rows:  # region shorter than one poll: take the nearest samples
             rows = sorted(self.samples, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))[:3]
+        if not rows:  # NVML refused to answer (e.g. the process runs under a profiler)
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["no NVML samples"], "samples": 0, "how": how}
         mask = 0
         for r in rows:
             mask |= r[3]

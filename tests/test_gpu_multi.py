@@ -1,0 +1,77 @@
+"""Multi-GPU reduction path (needs >= 2 GPUs: `gpurun --gpus 2`): one process per GPU, contiguous
+slices, local two-pass sums, NCCL all-gather of one scalar per rank, rank-ordered fold on the
+device — bit-identical on every rank and equal to the order restated by the oracle."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+pytestmark = pytest.mark.gpu
+
+
+def _rank(rank: int, world: int, uid: bytes, n: int, out_dir: str):
+    sys.path.insert(0, str(ROOT))
+    from custos_b200 import _native as N
+    from custos_b200.raw import Comm, RawDevice, shard_range
+    from custos_b200.workloads import CHEAP8
+
+    dev = RawDevice(rank)
+    comm = Comm(dev, world, rank, uid)
+    x = np.random.default_rng(5).uniform(-1, 1, n).astype(np.float32)
+    b, e = shard_range(n, 4, world, rank)
+    local = x[b:e]
+    p = dev.upload(local)
+    out = dev.alloc(64)
+    res = {}
+    for name in ("sum", "mean"):
+        if name == "sum":
+            comm.sum_into(N.F32, p, local.size, out)
+        else:
+            comm.mean_into(N.F32, p, local.size, n, out)
+        res[name] = dev.d2h(out, 1, N.F32)[0]
+    again = []
+    for _ in range(5):  # run-to-run determinism
+        comm.sum_into(N.F32, p, local.size, out)
+        again.append(dev.d2h(out, 1, N.F32)[0].tobytes())
+    assert len(set(again)) == 1 and again[0] == res["sum"].tobytes()
+    # element-wise work on the slice: no communication
+    q = dev.alloc(local.nbytes)
+    dev.apply(dev.compile(CHEAP8, N.F32), p, q, local.size)
+    np.save(f"{out_dir}/out{rank}.npy", dev.d2h(q, local.size, N.F32))
+    np.save(f"{out_dir}/r{rank}.npy", np.array([res["sum"], res["mean"]], np.float32))
+    comm.close()
+    dev.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_sum_over_nccl(tmp_path, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from custos_b200 import _native as N
+    from custos_b200.raw import Comm, shard_range, sum_plan
+    from custos_b200.workloads import CHEAP8
+    from oracle import oracle as orc
+    n = (1 << 24) + 1001
+    uid = Comm.unique_id()
+    mp.spawn(_rank, args=(world, uid, n, str(tmp_path)), nprocs=world, join=True)
+    x = np.random.default_rng(5).uniform(-1, 1, n).astype(np.float32)
+    partials = []
+    for r in range(world):
+        b, e = shard_range(n, 4, world, r)
+        plan = sum_plan(N.F32, e - b)
+        partials.append(orc.sum_two_pass(orc.F32, x[b:e], plan["blocks"], plan["chunk"], plan["threads"], plan["vec"], plan["threads2"]))
+    want = partials[0]
+    for p in partials[1:]:
+        want = np.float32(want + p)
+    rows = [np.load(tmp_path / f"r{r}.npy") for r in range(world)]
+    for r in range(world):
+        assert rows[r][0].tobytes() == want.tobytes(), (r, rows[r][0], want)
+        assert rows[r][1].tobytes() == np.float32(want / np.float32(n)).tobytes()
+    assert abs(float(want) - orc.sum_f64(orc.F32, x)) <= 1e-6 * float(np.sum(np.abs(x.astype(np.float64))))
+    full = np.concatenate([np.load(tmp_path / f"out{r}.npy") for r in range(world)])
+    assert np.array_equal(full.view(np.uint32), orc.apply_chain(CHEAP8, orc.F32, x).view(np.uint32))
