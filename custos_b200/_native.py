@@ -73,6 +73,7 @@ SIGNATURES = {
     "cb_apply": [_vp, _vp, _u64, _u64, _sz],
     "cb_unary_grad": [_vp, _vp, _u64, _u64, _u64, _sz],
     "cb_apply2": [_vp, _vp, _u64, _u64, _u64, _sz],
+    "cb_apply_host": [_vp, _vp, _vp, _vp, _sz],
     "cb_binary": [_vp, _i32, _i32, _u64, _u64, _u64, _sz],
     "cb_sum": [_vp, _i32, _u64, _sz, _u64],
     "cb_mean": [_vp, _i32, _u64, _sz, _u64],

@@ -97,6 +97,16 @@ struct cb_device {
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     size_t stage_bytes = 0;
 
+    // host-operand pipeline (cb_apply_host): a ring of device chunks and a third stream for D2H
+    static constexpr int kPipeSlots = 3;
+    cudaStream_t d2h_stream = nullptr;
+    size_t pipe_chunk_bytes = 0;
+    void *pipe_in[kPipeSlots] = {nullptr, nullptr, nullptr};
+    void *pipe_out[kPipeSlots] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_h2d[kPipeSlots] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_k[kPipeSlots] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_d2h[kPipeSlots] = {nullptr, nullptr, nullptr};
+
     // reduction scratch
     void *sum_partials = nullptr;  // kSumMaxBlocks x 8 bytes
     void *sum_scalar = nullptr;    // 8 bytes device

@@ -183,6 +183,10 @@ class RawDevice:
     def unary_grad(self, e: Expr, lhs: int, lhs_grad: int, out_grad: int, n: int):
         N.call("cb_unary_grad", self.h, e.handle, lhs, lhs_grad, out_grad, n)
 
+    def apply_host(self, e: Expr, host_in: int, host_out: int, n: int):
+        """out_host[i] = f(in_host[i]) with H2D / kernel / D2H overlapped chunk by chunk (raw host addresses)."""
+        N.call("cb_apply_host", self.h, e.handle, C.c_void_p(host_in), C.c_void_p(host_out), n)
+
     def apply2(self, e: Expr, lhs: int, rhs: int, out: int, n: int):
         N.call("cb_apply2", self.h, e.handle, lhs, rhs, out, n)
 

@@ -216,6 +216,14 @@ int32_t cb_unary_grad(cb_device *dev, cb_expr *g, uint64_t lhs, uint64_t lhs_gra
 /* two-marker expression: out[i] = f(lhs[i], rhs[i]) */
 int32_t cb_apply2(cb_device *dev, cb_expr *f, uint64_t lhs, uint64_t rhs, uint64_t out, size_t n);
 
+/* Host-resident operands: out_host[i] = f(in_host[i]).  The reference's end-to-end path is
+ * alloc_from_slice (pageable H2D, src/devices/cuda/cuda.rs:124-137) -> kernel -> read (D2H + two stream
+ * syncs, src/devices/cuda/ops.rs:32-48), strictly one after the other.  Here the buffer is cut into
+ * chunks that flow through three streams, so H2D of chunk i+1, the kernel of chunk i and D2H of chunk
+ * i-1 overlap (full-duplex PCIe).  Pinned host memory (cb_host_alloc) gets the overlapped path,
+ * pageable memory falls back to the staged serial one.  Synchronises before returning. */
+int32_t cb_apply_host(cb_device *dev, cb_expr *f, const void *in_host, void *out_host, size_t n);
+
 /* Binary element-wise add/mul/sub/div — the `AddEw`/`MulBuf` pattern
  * (README.md:96-122, tests/demo_impl/cuda/mod.rs:3-36, src/lib.rs:293-301). */
 typedef enum cb_binop { CB_BIN_ADD = 0, CB_BIN_MUL = 1, CB_BIN_SUB = 2, CB_BIN_DIV = 3 } cb_binop;
