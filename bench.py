@@ -349,8 +349,14 @@ def extra_workloads(dev, n):
     row("cheap8_f32", timeit(lambda: dev.apply(cheap, a, c, n)), 8)
     chain = dev.compile(CHAIN8, N.F32)
     row("chain8_f32", timeit(lambda: dev.apply(chain, a, c, n)), 8)
+    h16 = np.random.default_rng(4).uniform(-4, 4, 1 << 24).astype(np.float16)
+    ph = dev.upload(h16)
+    for off in range(0, n, 1 << 24):  # proper binary16 inputs in `c`'s first half, results into `b`
+        dev.copy(N.F16, c, off, ph, 0, min(1 << 24, n - off))
+    dev.free(ph)
     chain16 = dev.compile(CHAIN8, N.F16)
-    row("chain8_f16", timeit(lambda: dev.apply(chain16, a, c, n)), 4)
+    row("chain8_f16", timeit(lambda: dev.apply(chain16, c, b, n)), 4)
+    dev.fill(N.F32, b, n, 0.25)
     row("binary_add_f32", timeit(lambda: dev.binary(N.F32, N.BIN_ADD, a, b, c, n)), 12)
     row("binary_mul_f32", timeit(lambda: dev.binary(N.F32, N.BIN_MUL, a, b, c, n)), 12)
     g = dev.compile(CHAIN8_GRADS[3], N.F32, N.KERNEL_UNARY_GRAD)

@@ -316,6 +316,54 @@ std::string expr_cuda_function(int32_t dtype, const cb_node *const *progs, const
         }
         s += "    return x;\n}\n#endif\n";
     }
+    if (dtype == CB_F16) {
+        // two binary16 elements per 32-bit word (skeleton.cuh: cbw_*); ops with a literal operand take the
+        // mixed-precision forms that need no unpack
+        auto f32_bits_of = [](const cb_node &c, bool negate) {
+            float f = host_f16_to_f32(host_f32_to_f16((float)c.fimm));
+            if (negate) f = -f;
+            uint32_t u;
+            std::memcpy(&u, &f, 4);
+            char buf[48];
+            std::snprintf(buf, sizeof buf, "__uint_as_float(0x%08xu)", u);
+            return std::string(buf);
+        };
+        auto half_bits_of = [](const cb_node &c) {
+            char buf[32];
+            std::snprintf(buf, sizeof buf, "(T)0x%04xu", (unsigned)host_f32_to_f16((float)c.fimm));
+            return std::string(buf);
+        };
+        s += "#if CB_PAIR\n__device__ __forceinline__ cb_w cb_fnw(cb_w x, cb_w y, bool &redo)\n{\n";
+        for (int32_t k = 0; k < n_progs; k++) {
+            const cb_node *nd = progs[k];
+            const int32_t n = n_nodes[k];
+            s += "    { // op " + std::to_string(k) + "\n";
+            for (int32_t i = 0; i < n; i++) {
+                const cb_node &c = nd[i];
+                const std::string ta = "t" + std::to_string(c.a), tb = "t" + std::to_string(c.b);
+                const bool a_const = c.a >= 0 && nd[c.a].op == CB_OP_CONST, b_const = c.b >= 0 && nd[c.b].op == CB_OP_CONST;
+                std::string rhs;
+                if (c.op == CB_OP_X) rhs = "x";
+                else if (c.op == CB_OP_Y) rhs = "y";
+                else if (c.op == CB_OP_CONST) {
+                    char buf[32];
+                    std::snprintf(buf, sizeof buf, "cbw_lit(0x%04xu)", (unsigned)host_f32_to_f16((float)c.fimm));
+                    rhs = buf;
+                } else if (c.op == CB_OP_ADD && b_const) rhs = "cbw_add_c(" + ta + ", " + f32_bits_of(nd[c.b], false) + ")";
+                else if (c.op == CB_OP_ADD && a_const) rhs = "cbw_add_c(" + tb + ", " + f32_bits_of(nd[c.a], false) + ")";
+                else if (c.op == CB_OP_SUB && b_const) rhs = "cbw_add_c(" + ta + ", " + f32_bits_of(nd[c.b], true) + ")";
+                else if (c.op == CB_OP_MUL && b_const) rhs = "cbw_mul_c(" + ta + ", " + half_bits_of(nd[c.b]) + ")";
+                else if (c.op == CB_OP_MUL && a_const) rhs = "cbw_mul_c(" + tb + ", " + half_bits_of(nd[c.a]) + ")";
+                else if (c.op == CB_OP_SIN || c.op == CB_OP_COS || c.op == CB_OP_TAN)
+                    rhs = "cbw_" + std::string(cuda_fn(c.op) + 3) + "(" + ta + ", redo)";
+                else if (op_is_binary(c.op)) rhs = "cbw_" + std::string(cuda_fn(c.op) + 3) + "(" + ta + ", " + tb + ")";
+                else rhs = "cbw_" + std::string(cuda_fn(c.op) + 3) + "(" + ta + ")";
+                s += "        const cb_w t" + std::to_string(i) + " = " + rhs + ";\n";
+            }
+            s += "        x = t" + std::to_string(n - 1) + ";\n    }\n";
+        }
+        s += "    return x;\n}\n#endif\n";
+    }
     s += "}  // namespace CB_NS\n";
     return s;
 }
