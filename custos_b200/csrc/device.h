@@ -43,7 +43,7 @@ namespace cb {
 struct Tunables {
     int threads = 256;
     int unroll = 4;
-    int min_blocks = 4;
+    int min_blocks = 5;  // __launch_bounds__ second argument: <= 48 registers, 5 resident blocks (profiles/r1_perf_ab4.log)
     int blocks_per_sm = 8;
     int waves = 16;  // CB_WAVES: grid cap = SMs x resident blocks x waves; >1 lets the hardware rebalance
                      // SMs that run slower (a single static wave left ~10% on the table, profiles/r1_tuning.md)
