@@ -94,6 +94,7 @@ SIGNATURES = {
     "cb_comm_unique_id": [C.c_char_p],
     "cb_comm_create": [_vp, _i32, _i32, C.c_char_p, _P(_vp)],
     "cb_comm_destroy": [_vp],
+    "cb_comm_uses_peer_memory": [_vp, _P(_i32)],
     "cb_comm_sum": [_vp, _i32, _u64, _sz, _u64],
     "cb_comm_mean": [_vp, _i32, _u64, _sz, _sz, _u64],
     "cb_shard_range": [_sz, _i32, _i32, _i32, _P(_sz), _P(_sz)],

@@ -12,8 +12,10 @@
 // torch process the already loaded libnccl.so.2 is reused.
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <vector>
 
 #include "device.h"
 
@@ -66,7 +68,91 @@ struct cb_comm {
     int n_ranks = 1, rank = 0;
     void *local = nullptr;     // this rank's partial (8 bytes)
     void *gathered = nullptr;  // n_ranks partials
+    // peer-memory exchange (fused pass 2 + exchange kernel); NCCL is only used to set it up
+    bool p2p = false;
+    cb::XchgSlot *xchg = nullptr;                 // this rank's buffer: 2 parities x n_ranks slots
+    std::vector<void *> opened;                   // peers' buffers mapped through CUDA IPC
+    cb::XchgSlot **peer_tbl = nullptr;            // device array of n_ranks buffer addresses
+    int *status = nullptr;                        // device flag: a peer timed out
+    unsigned long long epoch = 0;
 };
+
+// Maps every rank's exchange buffer into this process.  Returns false (and leaves the communicator on the
+// NCCL path) if any step is unavailable on ANY rank; the decision is taken collectively.
+static bool setup_p2p(cb_comm *c)
+{
+    if (const char *v = std::getenv("CB_COMM_P2P"))
+        if (v[0] == '0') return false;
+    if (c->n_ranks > cb::kMaxRanks) return false;
+    const size_t bytes = sizeof(cb::XchgSlot) * 2 * (size_t)c->n_ranks;
+    bool ok = cudaMalloc(reinterpret_cast<void **>(&c->xchg), bytes) == cudaSuccess &&
+              cudaMemset(c->xchg, 0, bytes) == cudaSuccess && cudaMalloc(reinterpret_cast<void **>(&c->status), sizeof(int)) == cudaSuccess &&
+              cudaMemset(c->status, 0, sizeof(int)) == cudaSuccess;
+    cudaIpcMemHandle_t mine;
+    std::memset(&mine, 0, sizeof mine);
+    ok = ok && cudaIpcGetMemHandle(&mine, c->xchg) == cudaSuccess;
+    // all-gather {ok flag, handle} through NCCL (bytes)
+    struct Msg {
+        unsigned char ok;
+        unsigned char pad[7];
+        cudaIpcMemHandle_t h;
+    } msg;
+    std::memset(&msg, 0, sizeof msg);
+    msg.ok = ok ? 1 : 0;
+    msg.h = mine;
+    void *d_send = nullptr, *d_recv = nullptr;
+    std::vector<Msg> all((size_t)c->n_ranks);
+    bool comm_ok = cudaMalloc(&d_send, sizeof(Msg)) == cudaSuccess && cudaMalloc(&d_recv, sizeof(Msg) * (size_t)c->n_ranks) == cudaSuccess &&
+                   cudaMemcpy(d_send, &msg, sizeof(Msg), cudaMemcpyHostToDevice) == cudaSuccess &&
+                   nccl().AllGather(d_send, d_recv, sizeof(Msg), /*ncclUint8*/ 1, c->comm, c->dev->stream) == ncclSuccess &&
+                   cudaStreamSynchronize(c->dev->stream) == cudaSuccess &&
+                   cudaMemcpy(all.data(), d_recv, sizeof(Msg) * (size_t)c->n_ranks, cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (d_send) cudaFree(d_send);
+    if (d_recv) cudaFree(d_recv);
+    if (!comm_ok) {
+        cudaGetLastError();
+        return false;
+    }
+    for (const Msg &m : all) ok = ok && m.ok;
+    std::vector<cb::XchgSlot *> tbl((size_t)c->n_ranks, nullptr);
+    if (ok) {
+        for (int r = 0; r < c->n_ranks && ok; r++) {
+            if (r == c->rank) {
+                tbl[(size_t)r] = c->xchg;
+                continue;
+            }
+            void *p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[(size_t)r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                ok = false;
+                break;
+            }
+            c->opened.push_back(p);
+            tbl[(size_t)r] = static_cast<cb::XchgSlot *>(p);
+        }
+    }
+    // second collective decision: did every rank manage to open every handle?
+    unsigned char flag = ok ? 1 : 0;
+    std::vector<unsigned char> flags((size_t)c->n_ranks, 0);
+    void *d1 = nullptr, *dn = nullptr;
+    comm_ok = cudaMalloc(&d1, 8) == cudaSuccess && cudaMalloc(&dn, (size_t)c->n_ranks + 8) == cudaSuccess &&
+              cudaMemcpy(d1, &flag, 1, cudaMemcpyHostToDevice) == cudaSuccess &&
+              nccl().AllGather(d1, dn, 1, 1, c->comm, c->dev->stream) == ncclSuccess &&
+              cudaStreamSynchronize(c->dev->stream) == cudaSuccess &&
+              cudaMemcpy(flags.data(), dn, (size_t)c->n_ranks, cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (d1) cudaFree(d1);
+    if (dn) cudaFree(dn);
+    for (unsigned char f : flags) ok = ok && f;
+    if (!comm_ok || !ok) {
+        cudaGetLastError();
+        return false;
+    }
+    if (cudaMalloc(reinterpret_cast<void **>(&c->peer_tbl), sizeof(void *) * (size_t)c->n_ranks) != cudaSuccess ||
+        cudaMemcpy(c->peer_tbl, tbl.data(), sizeof(void *) * (size_t)c->n_ranks, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError();
+        return false;  // cannot happen on one rank only in practice; the NCCL path still works everywhere
+    }
+    return true;
+}
 
 using cb::fail;
 
@@ -103,7 +189,15 @@ extern "C" int32_t cb_comm_create(cb_device *dev, int32_t n_ranks, int32_t rank,
         nccl().CommDestroy(c->comm);
         return dev->cuda_fail(e, "cudaMalloc (comm scratch)");
     }
+    c->p2p = setup_p2p(c.get());
     *out = c.release();
+    return CB_OK;
+}
+
+extern "C" int32_t cb_comm_uses_peer_memory(cb_comm *c, int32_t *flag)
+{
+    CB_CHECK_ARG(c && flag, "null argument");
+    *flag = c->p2p ? 1 : 0;
     return CB_OK;
 }
 
@@ -112,6 +206,10 @@ extern "C" int32_t cb_comm_destroy(cb_comm *c)
     if (!c) return CB_OK;
     c->dev->use();
     cudaStreamSynchronize(c->dev->stream);
+    for (void *p : c->opened) cudaIpcCloseMemHandle(p);
+    if (c->peer_tbl) cudaFree(c->peer_tbl);
+    if (c->status) cudaFree(c->status);
+    if (c->xchg) cudaFree(c->xchg);
     if (c->comm) nccl().CommDestroy(c->comm);
     if (c->local) cudaFree(c->local);
     if (c->gathered) cudaFree(c->gathered);
@@ -124,6 +222,23 @@ static int32_t comm_reduce(cb_comm *c, int32_t dtype, uint64_t in, size_t n_loca
     CB_CHECK_ARG(c && cb::valid_dtype(dtype) && out, "bad argument");
     cb_device *dev = c->dev;
     CB_TRY(dev->use());
+    if (c->p2p) {
+        // pass 1 + ONE kernel that folds the partials, exchanges the totals over NVLink peer memory and
+        // folds them in rank order
+        cb::XchgArgs x;
+        x.peers = c->peer_tbl;
+        x.n_ranks = c->n_ranks;
+        x.rank = c->rank;
+        x.epoch = ++c->epoch;
+        x.timeout_cycles = 4000000000ll;  // ~2 s of SM clock
+        x.status = c->status;
+        if (n_local && !in) return fail(CB_ERR_INVALID_ARG, "null buffer");
+        cudaError_t e = cb::launch_sum_exchange(dev->ctx(), dtype, reinterpret_cast<const void *>(in), n_local, dev->sum_partials,
+                                                reinterpret_cast<void *>(out), divisor, x);
+        if (e != cudaSuccess) return dev->cuda_fail(e, "sum exchange kernels");
+        dev->launches += n_local ? 2 : 1;
+        return CB_OK;
+    }
     // a rank may own an empty slice (n smaller than the rank count): its partial is 0
     if (n_local == 0) {
         cudaError_t e = cudaMemsetAsync(c->local, 0, 8, dev->stream);

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstring>
 #include <type_traits>
 
 #include "kernels.h"
@@ -307,6 +308,73 @@ __global__ void fold_ranks_kernel(const ACC *gathered, int n_ranks, ACC *out, si
     }
 }
 
+// ---- fused pass 2 + cross-GPU exchange over NVLink peer memory -----------------------------------
+// Every rank owns a small exchange buffer that all peers map (CUDA IPC).  The single block that folds
+// the pass-1 partials also publishes the rank's total into every peer's buffer with system-scope
+// release stores (threads 0..R-1 each serve one peer: R NVLink stores in flight), waits for the R
+// totals addressed to this rank with acquire loads, and folds them in rank order.  One kernel instead
+// of pass 2 + ncclAllGather + fold: the exchange costs one NVLink round trip (~2-4 us), not a
+// collective launch.  Slots are double buffered by the parity of the call number: a rank can only be one
+// call ahead of a peer (it needs the peer's value to finish a call), so parity p of call k+2 is never
+// written before every rank has finished reading parity p of call k.
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <typename ACC>
+__global__ void __launch_bounds__(kThreads)
+sum_pass2_exchange_kernel(const ACC *partials, int nblocks, XchgSlot *const *peers, int n_ranks, int rank,
+                          unsigned long long epoch, ACC *out, size_t divisor, long long timeout_cycles, int *status)
+{
+    __shared__ ACC vals[kMaxRanks];
+    __shared__ ACC local;
+    ACC s = (ACC)0;
+    for (int i = threadIdx.x; i < nblocks; i += kThreads) s = acc_add<ACC>(s, partials[i]);
+    s = block_tree<ACC, kThreads>(s);
+    if (threadIdx.x == 0) local = s;
+    __syncthreads();
+    const int parity = (int)(epoch & 1ull);
+    if ((int)threadIdx.x < n_ranks) {
+        const int r = threadIdx.x;
+        unsigned long long bits = 0;
+        const ACC mine = local;
+        memcpy(&bits, &mine, sizeof(ACC));
+        XchgSlot *dst = peers[r] + parity * n_ranks + rank;  // my slot in rank r's buffer (peer memory)
+        *reinterpret_cast<volatile unsigned long long *>(&dst->value) = bits;
+        st_release_sys(&dst->epoch, epoch);
+        const XchgSlot *src = peers[rank] + parity * n_ranks + r;  // rank r's slot in my buffer
+        const long long t0 = clock64();
+        bool ok = true;
+        while (ld_acquire_sys(&src->epoch) != epoch) {
+            if (clock64() - t0 > timeout_cycles) {  // a peer never arrived: fail instead of hanging the GPU
+                ok = false;
+                break;
+            }
+        }
+        unsigned long long got = *reinterpret_cast<const volatile unsigned long long *>(&src->value);
+        if (!ok) {
+            got = 0;
+            atomicExch(status, 1);
+        }
+        ACC v;
+        memcpy(&v, &got, sizeof(ACC));
+        vals[r] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ACC t = vals[0];
+        for (int r = 1; r < n_ranks; r++) t = acc_add<ACC>(t, vals[r]);  // rank order, like fold_ranks_kernel
+        *out = divisor ? t / (ACC)divisor : t;
+    }
+}
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 inline int grid_for(size_t work_items, size_t per_block, int max_blocks)
@@ -341,6 +409,26 @@ cudaError_t launch_binary_op(const LaunchCtx &ctx, int op, const void *lhs, cons
     case CB_BIN_SUB: return launch_binary_t<T, CB_BIN_SUB>(ctx, lhs, rhs, out, n);
     default: return launch_binary_t<T, CB_BIN_DIV>(ctx, lhs, rhs, out, n);
     }
+}
+
+template <typename T, typename ACC>
+cudaError_t launch_sum_xchg_t(const LaunchCtx &ctx, const void *in, size_t n, int blocks, size_t chunk, void *partials,
+                              void *out, size_t divisor, const XchgArgs &x)
+{
+    if (n == 0) {  // an empty slice contributes 0 but still takes part in the exchange
+        cudaError_t e = cudaMemsetAsync(partials, 0, sizeof(ACC), ctx.stream);
+        if (e != cudaSuccess) return e;
+        blocks = 1;
+    } else if (aligned16(in)) {
+        sum_pass1_kernel<T, ACC, true, 4><<<blocks, kThreads, 0, ctx.stream>>>((const T *)in, n, chunk, (ACC *)partials);
+    } else {
+        sum_pass1_kernel<T, ACC, false, 1><<<blocks, kThreads, 0, ctx.stream>>>((const T *)in, n, chunk, (ACC *)partials);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    sum_pass2_exchange_kernel<ACC><<<1, kThreads, 0, ctx.stream>>>((const ACC *)partials, blocks, x.peers, x.n_ranks, x.rank,
+                                                                   x.epoch, (ACC *)out, divisor, x.timeout_cycles, x.status);
+    return cudaGetLastError();
 }
 
 template <typename T, typename ACC>
@@ -483,6 +571,25 @@ cudaError_t launch_sum(const LaunchCtx &ctx, int dtype, const void *in, size_t n
     case CB_I64: return launch_sum_t<long long, long long>(ctx, in, n, blocks, chunk, partials, out, divisor);
     case CB_U32: return launch_sum_t<unsigned int, long long>(ctx, in, n, blocks, chunk, partials, out, divisor);
     case CB_U8: return launch_sum_t<unsigned char, long long>(ctx, in, n, blocks, chunk, partials, out, divisor);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_sum_exchange(const LaunchCtx &ctx, int dtype, const void *in, size_t n, void *partials, void *out,
+                                size_t divisor, const XchgArgs &x)
+{
+    (void)cudaGetLastError();
+    int blocks = 1, threads, vec, threads2;
+    size_t chunk = 0;
+    if (n) sum_plan(dtype, n, &blocks, &chunk, &threads, &vec, &threads2);
+    switch (dtype) {
+    case CB_F32: return launch_sum_xchg_t<float, float>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
+    case CB_F64: return launch_sum_xchg_t<double, double>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
+    case CB_F16: return launch_sum_xchg_t<half_bits, float>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
+    case CB_I32: return launch_sum_xchg_t<int, long long>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
+    case CB_I64: return launch_sum_xchg_t<long long, long long>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
+    case CB_U32: return launch_sum_xchg_t<unsigned int, long long>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
+    case CB_U8: return launch_sum_xchg_t<unsigned char, long long>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
     default: return cudaErrorInvalidValue;
     }
 }

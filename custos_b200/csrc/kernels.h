@@ -25,6 +25,21 @@ int launch_copy_count(const void *dst, const void *src, size_t bytes);
 void sum_plan(int dtype, size_t n, int *blocks, size_t *chunk, int *threads, int *vec, int *threads2);
 // partials: device scratch of kSumMaxBlocks accumulators; out: device scalar of the accumulation type
 cudaError_t launch_sum(const LaunchCtx &ctx, int dtype, const void *in, size_t n, void *partials, void *out, size_t divisor);
+// cross-GPU exchange of reduction totals through peer-mapped memory (see kernels.cu)
+constexpr int kMaxRanks = 64;
+struct XchgSlot {
+    unsigned long long value;  // bit pattern of the rank's total (accumulation type)
+    unsigned long long epoch;  // call number that wrote it
+};
+struct XchgArgs {
+    XchgSlot *const *peers;  // device array: peers[r] = rank r's exchange buffer (2 x n_ranks slots), peer mapped
+    int n_ranks, rank;
+    unsigned long long epoch;
+    long long timeout_cycles;
+    int *status;  // set to 1 by the kernel when a peer never arrived
+};
+cudaError_t launch_sum_exchange(const LaunchCtx &ctx, int dtype, const void *in, size_t n, void *partials, void *out,
+                                size_t divisor, const XchgArgs &x);
 cudaError_t launch_fold_ranks(const LaunchCtx &ctx, int dtype, const void *gathered, int n_ranks, void *out, size_t divisor);
 
 }  // namespace cb

@@ -257,6 +257,12 @@ class Comm:
         N.call("cb_comm_unique_id", buf)
         return buf.raw
 
+    @property
+    def uses_peer_memory(self) -> bool:
+        v = C.c_int32()
+        N.call("cb_comm_uses_peer_memory", self.h, C.byref(v))
+        return bool(v.value)
+
     def sum_into(self, dtype, dptr: int, n_local: int, out_dptr: int):
         N.call("cb_comm_sum", self.h, dtype_code(dtype), dptr, n_local, out_dptr)
 

@@ -271,14 +271,20 @@ int32_t cb_launch_count(cb_device *dev, uint64_t *count);
 
 /* ------------------------------------------------------ multi-GPU (NCCL) */
 /* One process per GPU.  Element-wise work needs no communication; only the
- * reduction partials are exchanged: all-gather of one scalar per rank followed
- * by a rank-ordered fold on every rank (deterministic). */
+ * reduction totals are exchanged — one scalar per rank, folded in rank order on every
+ * rank (deterministic).  The exchange is fused into the last reduction kernel: it writes
+ * the rank's total into every peer's buffer over NVLink (peer memory mapped through CUDA
+ * IPC, system-scope release/acquire) and waits for the peers' totals; NCCL sets the
+ * mapping up and remains the fallback (all-gather + fold). */
 typedef struct cb_comm cb_comm;
 #define CB_COMM_ID_BYTES 128
 int32_t cb_comm_unique_id(uint8_t id[CB_COMM_ID_BYTES]);
 int32_t cb_comm_create(cb_device *dev, int32_t n_ranks, int32_t rank,
                        const uint8_t id[CB_COMM_ID_BYTES], cb_comm **out);
 int32_t cb_comm_destroy(cb_comm *c);
+/* 1 when the totals are exchanged by the fused reduce+exchange kernel over NVLink peer memory (CUDA IPC),
+ * 0 when the communicator fell back to ncclAllGather + fold (CB_COMM_P2P=0 forces the fallback) */
+int32_t cb_comm_uses_peer_memory(cb_comm *c, int32_t *flag);
 /* local two-pass sum of `in`, then exchange + rank-ordered fold; out = device scalar */
 int32_t cb_comm_sum(cb_comm *c, int32_t dtype, uint64_t in, size_t n_local, uint64_t out);
 int32_t cb_comm_mean(cb_comm *c, int32_t dtype, uint64_t in, size_t n_local, size_t n_global,

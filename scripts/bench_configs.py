@@ -177,7 +177,8 @@ def sum_config(total):
     truth = full * float(np.sum(block.astype(np.float64))) + float(np.sum(block[:rem].astype(np.float64)))
     res = {"n_gpus": world, "elements": total, "ms": ms, "GB/s": total * 4 / (ms * 1e-3) / 1e9,
            "frac_of_measured_peak_x_gpus": total * 4 / (ms * 1e-3) / 1e9 / (PEAK * world),
-           "rel_err_vs_fp64": abs(got - truth) / truth, "sum": got}
+           "rel_err_vs_fp64": abs(got - truth) / truth, "sum": got,
+           "exchange": ("peer memory (fused kernel)" if comm and comm.uses_peer_memory else ("nccl all-gather" if comm else "none"))}
     if comm:
         comm.close()
     dev.close()

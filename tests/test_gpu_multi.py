@@ -13,14 +13,19 @@ ROOT = Path(__file__).resolve().parent.parent
 pytestmark = pytest.mark.gpu
 
 
-def _rank(rank: int, world: int, uid: bytes, n: int, out_dir: str):
+def _rank(rank: int, world: int, uid: bytes, uid_nccl: bytes, n: int, out_dir: str):
+    import os
     sys.path.insert(0, str(ROOT))
     from custos_b200 import _native as N
     from custos_b200.raw import Comm, RawDevice, shard_range
     from custos_b200.workloads import CHEAP8
 
     dev = RawDevice(rank)
-    comm = Comm(dev, world, rank, uid)
+    comm = Comm(dev, world, rank, uid)  # fused reduce + exchange over NVLink peer memory
+    os.environ["CB_COMM_P2P"] = "0"
+    comm_nccl = Comm(dev, world, rank, uid_nccl)  # the fallback: ncclAllGather + fold
+    del os.environ["CB_COMM_P2P"]
+    assert not comm_nccl.uses_peer_memory
     x = np.random.default_rng(5).uniform(-1, 1, n).astype(np.float32)
     b, e = shard_range(n, 4, world, rank)
     local = x[b:e]
@@ -38,6 +43,13 @@ def _rank(rank: int, world: int, uid: bytes, n: int, out_dir: str):
         comm.sum_into(N.F32, p, local.size, out)
         again.append(dev.d2h(out, 1, N.F32)[0].tobytes())
     assert len(set(again)) == 1 and again[0] == res["sum"].tobytes()
+    comm_nccl.sum_into(N.F32, p, local.size, out)  # both exchange paths fold in rank order: same bits
+    assert dev.d2h(out, 1, N.F32)[0].tobytes() == res["sum"].tobytes()
+    # an empty slice still takes part in the exchange
+    comm.sum_into(N.F32, p, local.size if rank else 0, out)
+    part0 = dev.d2h(out, 1, N.F32)[0]
+    np.save(f"{out_dir}/p2p{rank}.npy", np.array([1.0 if comm.uses_peer_memory else 0.0, float(part0)]))
+    comm_nccl.close()
     # element-wise work on the slice: no communication
     q = dev.alloc(local.nbytes)
     dev.apply(dev.compile(CHEAP8, N.F32), p, q, local.size)
@@ -57,8 +69,8 @@ def test_sharded_sum_over_nccl(tmp_path, world):
     from custos_b200.workloads import CHEAP8
     from oracle import oracle as orc
     n = (1 << 24) + 1001
-    uid = Comm.unique_id()
-    mp.spawn(_rank, args=(world, uid, n, str(tmp_path)), nprocs=world, join=True)
+    uid, uid_nccl = Comm.unique_id(), Comm.unique_id()
+    mp.spawn(_rank, args=(world, uid, uid_nccl, n, str(tmp_path)), nprocs=world, join=True)
     x = np.random.default_rng(5).uniform(-1, 1, n).astype(np.float32)
     partials = []
     for r in range(world):
@@ -73,5 +85,11 @@ def test_sharded_sum_over_nccl(tmp_path, world):
         assert rows[r][0].tobytes() == want.tobytes(), (r, rows[r][0], want)
         assert rows[r][1].tobytes() == np.float32(want / np.float32(n)).tobytes()
     assert abs(float(want) - orc.sum_f64(orc.F32, x)) <= 1e-6 * float(np.sum(np.abs(x.astype(np.float64))))
+    p2p = [np.load(tmp_path / f"p2p{r}.npy") for r in range(world)]
+    assert all(v[0] == 1.0 for v in p2p), "the peer-memory exchange was not used (CUDA IPC unavailable?)"
+    want_wo0 = np.float32(0)
+    for p in partials[1:]:
+        want_wo0 = np.float32(want_wo0 + p)
+    assert all(np.float32(v[1]) == want_wo0 for v in p2p)
     full = np.concatenate([np.load(tmp_path / f"out{r}.npy") for r in range(world)])
     assert np.array_equal(full.view(np.uint32), orc.apply_chain(CHEAP8, orc.F32, x).view(np.uint32))
