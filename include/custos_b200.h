@@ -295,7 +295,7 @@ int32_t cb_shard_range(size_t n, int32_t elem_bytes, int32_t n_ranks, int32_t ra
 
 /* ================================================================ module layer
  * A C++ restatement of custos' module stack around the device above
- * (Base, Cached, Lazy, Graph, Autograd: src/modules/*.rs), exported so that the
+ * (Base, Cached, Lazy, Graph, Autograd: the .rs files under src/modules), exported so that the
  * parity tests can drive `CUDA<Graph<Lazy<Autograd<Base>>>>`-style devices
  * without a Rust toolchain.  A Rust build would keep its own module layer and
  * bind only the functions above. */
