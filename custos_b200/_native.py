@@ -134,6 +134,7 @@ SIGNATURES = {
     "cbm_replay_kernel_nodes": [_vp, _P(_sz)],
     "cbm_optimize_mem_graph": [_vp],
     "cbm_unary_fusing": [_vp],
+    "cbm_elementwise_fusing": [_vp],
     "cbm_cache_traces": [_vp, _P(_i64), _sz, _P(_sz)],
     "cbm_cursor": [_vp, _P(_u64)],
     "cbm_set_cursor": [_vp, _u64],

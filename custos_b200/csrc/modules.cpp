@@ -63,7 +63,7 @@ struct Handle {
     bool owned = false;  // freed on drop (AllocFlag::None); cached and gradient buffers are not
 };
 
-enum class OpKind { NoOp, Apply, UnaryGrad, Binary };
+enum class OpKind { NoOp, Apply, UnaryGrad, Binary, Apply2 };
 
 // Operation (src/modules/lazy/lazy_graph.rs:8-12): argument ids + what to launch + the op hint
 struct Op {
@@ -75,7 +75,53 @@ struct Op {
     bool unary_hint = false;       // OpHint::Unary (src/op_hint.rs:5-11)
     bool fused = false;            // OpHint::UnaryFused
     std::vector<cb_node> hint;     // the closure of the hint, as IR
+    // what the op computes as ONE expression tree over its input buffers (X = in[0], Y = in[1]);
+    // kept for Apply and Binary ops so that element-wise fusing can splice producers into consumers
+    std::vector<uint64_t> in;
+    uint64_t out = 0;
+    std::vector<cb_node> tree;
 };
+
+cb_node mk_node(int32_t op, int32_t a = -1, int32_t b = -1)
+{
+    cb_node n;
+    std::memset(&n, 0, sizeof n);
+    n.op = op;
+    n.a = a;
+    n.b = b;
+    return n;
+}
+
+// `outer` with every `which` marker (CB_OP_X / CB_OP_Y) replaced by the value of `inner`; inner's markers
+// become inner_map[0/1], outer's other marker becomes outer_other_to.
+std::vector<cb_node> substitute(const std::vector<cb_node> &outer, int32_t which, int32_t outer_other_to,
+                                const std::vector<cb_node> &inner, const int32_t inner_map[2])
+{
+    std::vector<cb_node> r;
+    r.reserve(inner.size() + outer.size());
+    for (const cb_node &n : inner) {
+        cb_node c = n;
+        if (c.op == CB_OP_X) c.op = inner_map[0];
+        else if (c.op == CB_OP_Y) c.op = inner_map[1];
+        r.push_back(c);
+    }
+    const int32_t inner_root = (int32_t)r.size() - 1;
+    std::vector<int32_t> idx(outer.size(), -1);
+    for (size_t i = 0; i < outer.size(); i++) {
+        cb_node c = outer[i];
+        if (c.op == which) {
+            idx[i] = inner_root;
+            continue;
+        }
+        if (c.op == CB_OP_X || c.op == CB_OP_Y) c.op = outer_other_to;
+        if (c.a >= 0) c.a = idx[(size_t)c.a];
+        if (c.b >= 0) c.b = idx[(size_t)c.b];
+        idx[i] = (int32_t)r.size();
+        r.push_back(c);
+    }
+    if (idx.back() != (int32_t)r.size() - 1) r.push_back(mk_node(CB_OP_IDENTITY, idx.back()));  // outer was just the marker
+    return r;
+}
 
 // a grad function on the tape: the closure of unary_ew (src/unary.rs:118-128)
 struct GradOp {
@@ -219,6 +265,8 @@ int32_t call_op(cbm_device *d, const Op &op)
         return cb_unary_grad(d->raw, op.expr, arg[0]->ptr, arg[1]->ptr, arg[2]->ptr, arg[0]->len);
     case OpKind::Binary:  // args: (lhs, rhs, out)
         return cb_binary(d->raw, op.dtype, op.binop, arg[0]->ptr, arg[1]->ptr, arg[2]->ptr, arg[2]->len);
+    case OpKind::Apply2:  // args: (lhs, rhs, out): a fused two-input expression
+        return cb_apply2(d->raw, op.expr, arg[0]->ptr, arg[1]->ptr, arg[2]->ptr, arg[2]->len);
     default: return CB_OK;
     }
 }
@@ -557,6 +605,9 @@ extern "C" int32_t cbm_apply_fn(cbm_device *d, cbm_buf in, const cb_node *nodes,
     if (d->recording()) {  // Lazy::set_op_hint (lazy.rs:136-143); Base ignores hints (base.rs:86)
         op.unary_hint = true;
         op.hint.assign(nodes, nodes + n_nodes);
+        op.tree = op.hint;
+        op.in = {in_id};
+        op.out = out_id;
         d->op_of_id[out_id] = d->ops.size();
     }
     int32_t rc = add_op(d, std::move(op));
@@ -627,7 +678,12 @@ extern "C" int32_t cbm_binary(cbm_device *d, int32_t op, cbm_buf lhs, cbm_buf rh
     o.dtype = dtype;
     o.binop = op;
     o.arg_ids = {lid, rid, out_id};
-    if (d->recording()) d->op_of_id[out_id] = d->ops.size();
+    if (d->recording()) {
+        d->op_of_id[out_id] = d->ops.size();
+        o.in = {lid, rid};
+        o.out = out_id;
+        o.tree = {mk_node(CB_OP_X), mk_node(CB_OP_Y), mk_node(CB_OP_ADD + op, 0, 1)};
+    }
     int32_t rc = add_op(d, std::move(o));
     if (rc != CB_OK) return rc;
     *out = ob;
@@ -768,6 +824,7 @@ extern "C" int32_t cbm_op_hint_src(cbm_device *d, size_t i, char *out, size_t ca
     const Op &op = d->ops[i];
     std::string s;
     if (op.unary_hint) s = expr_to_cl_source(op.dtype, op.hint.data(), (int32_t)op.hint.size(), "x", "y");
+    else if (op.fused && op.kind == OpKind::Apply2) s = "Fused: " + expr_to_cl_source(op.dtype, op.tree.data(), (int32_t)op.tree.size(), "x", "y");
     else if (op.fused) s = "UnaryFused";
     if (s.size() + 1 > cap) return fail(CB_ERR_INVALID_ARG, "output buffer too small");
     std::memcpy(out, s.c_str(), s.size() + 1);
@@ -914,7 +971,13 @@ extern "C" int32_t cbm_unary_fusing(cbm_device *d)
                 cb_expr *fused = nullptr;
                 CB_TRY(cb_expr_compile(d->raw, dtype, CB_KERNEL_APPLY, progs.data(), counts.data(), (int32_t)progs.size(), &fused));
                 const uint64_t out_id = last.arg_ids[0], in_id = first.arg_ids[1];
-                for (size_t k = i + 1; k < j; k++) d->ops[(size_t)op_idx[k]] = Op();  // Operation::no_op()
+                std::vector<cb_node> tree = d->ops[(size_t)op_idx[i]].tree;
+                const int32_t xmap[2] = {CB_OP_X, CB_OP_X};
+                for (size_t k = i + 1; k < j; k++) tree = substitute(d->ops[(size_t)op_idx[k]].tree, CB_OP_X, CB_OP_X, tree, xmap);
+                for (size_t k = i + 1; k < j; k++) d->ops[(size_t)op_idx[k]] = Op();
+                first.tree = std::move(tree);
+                first.in = {in_id};
+                first.out = out_id;
                 first.expr = fused;
                 first.arg_ids = {out_id, in_id};
                 first.unary_hint = false;
@@ -923,6 +986,107 @@ extern "C" int32_t cbm_unary_fusing(cbm_device *d)
             }
             i = j;
         }
+    }
+    d->invalidate_replay();
+    return CB_OK;
+}
+
+// Element-wise fusing (not in the reference, which only fuses unary chains):
+// a producer op whose result is read by exactly ONE later op is spliced into that consumer as long as
+// the merged expression reads at most two distinct buffers, so `add(sin(a), cos(b))` or a binary op
+// followed by a unary chain becomes one kernel and one HBM round trip.  The same rules as for unary
+// fusing apply to what is skipped: checkpointed buffers, buffers of another length or dtype, buffers a
+// grad function needs.  Intermediates that are fused away are never written (they keep the zeros of
+// their allocation), exactly like the middle buffers of a fused unary chain (src/op_hint.rs:172-196).
+// Call it before optimize_mem_graph (aliasing makes ids share storage).
+extern "C" int32_t cbm_elementwise_fusing(cbm_device *d)
+{
+    CB_CHECK_ARG(d, "null device");
+    if (!d->has(CBM_GRAPH)) return fail(CB_ERR_MISSING_CACHE_TRACES, "MissingCacheTraces: no Graph module");
+    if (!d->has(CBM_LAZY)) return fail(CB_ERR_UNSUPPORTED, "UnaryFusingUnsupported: only Lazy records operations");
+    auto reads = [](const Op &o, uint64_t id) {
+        if (o.kind == OpKind::NoOp) return false;
+        if (o.kind == OpKind::UnaryGrad) return std::find(o.arg_ids.begin(), o.arg_ids.end(), id) != o.arg_ids.end();
+        return std::find(o.in.begin(), o.in.end(), id) != o.in.end();
+    };
+    auto writes = [](const Op &o, uint64_t id) {
+        if (o.kind == OpKind::NoOp) return false;
+        if (o.kind == OpKind::UnaryGrad) return o.arg_ids.size() > 1 && o.arg_ids[1] == id;
+        return o.out == id;
+    };
+    auto fusable = [](const Op &o) { return (o.kind == OpKind::Apply || o.kind == OpKind::Binary || o.kind == OpKind::Apply2) && !o.tree.empty(); };
+    std::vector<char> changed(d->ops.size(), 0);
+    for (size_t c = 0; c < d->ops.size(); c++) {
+        bool again = true;
+        while (again && fusable(d->ops[c])) {
+            again = false;
+            Op &oc = d->ops[c];
+            for (size_t slot = 0; slot < oc.in.size() && !again; slot++) {
+                const uint64_t B = oc.in[slot];
+                auto po = d->op_of_id.find(B);
+                if (po == d->op_of_id.end() || po->second >= c) continue;
+                const size_t p = po->second;
+                const Op &op = d->ops[p];
+                if (!fusable(op) || op.out != B || op.dtype != oc.dtype) continue;
+                const Entry *eb = d->resolve(B);
+                auto gi = d->buf_id_to_idx.find(B);
+                if (gi == d->buf_id_to_idx.end() || d->graph.node(gi->second).skip) continue;  // checkpoint()
+                auto go = d->buf_id_to_idx.find(oc.out);
+                if (go == d->buf_id_to_idx.end() || d->graph.node(go->second).len != d->graph.node(gi->second).len) continue;
+                (void)eb;
+                // exactly one reader, nobody else writes it, no grad function needs it
+                size_t n_readers = 0, n_writers = 0;
+                for (const Op &o : d->ops) {
+                    n_readers += reads(o, B) ? 1 : 0;
+                    n_writers += writes(o, B) ? 1 : 0;
+                }
+                bool on_tape = false;
+                for (const GradOp &g : d->tape) on_tape = on_tape || g.buf_id == B || g.out_id == B;
+                if (n_readers != 1 || n_writers != 1 || on_tape) continue;
+                // moving the producer down to the consumer must not cross a write to one of its inputs
+                bool hazard = false;
+                for (size_t q = p + 1; q < c && !hazard; q++)
+                    for (uint64_t pin : op.in) hazard = hazard || writes(d->ops[q], pin);
+                if (hazard) continue;
+                // merged input list: the consumer's other input (if any) first, then the producer's
+                std::vector<uint64_t> merged;
+                for (size_t k = 0; k < oc.in.size(); k++)
+                    if (k != slot) merged.push_back(oc.in[k]);
+                for (uint64_t pin : op.in)
+                    if (std::find(merged.begin(), merged.end(), pin) == merged.end()) merged.push_back(pin);
+                if (merged.size() > 2 || op.tree.size() + oc.tree.size() > (size_t)kMaxNodes) continue;
+                auto marker_of = [&merged](uint64_t id) {
+                    return (int32_t)(std::find(merged.begin(), merged.end(), id) - merged.begin()) == 0 ? CB_OP_X : CB_OP_Y;
+                };
+                const int32_t inner_map[2] = {marker_of(op.in[0]), op.in.size() > 1 ? marker_of(op.in[1]) : CB_OP_X};
+                const int32_t other_to = oc.in.size() > 1 ? marker_of(oc.in[1 - slot]) : CB_OP_X;
+                std::vector<cb_node> tree = substitute(oc.tree, slot == 0 ? CB_OP_X : CB_OP_Y, other_to, op.tree, inner_map);
+                oc.tree = std::move(tree);
+                oc.in = merged;
+                d->ops[p] = Op();  // Operation::no_op()
+                d->op_of_id.erase(B);
+                changed[c] = 1;
+                again = true;
+            }
+        }
+    }
+    for (size_t c = 0; c < d->ops.size(); c++) {
+        if (!changed[c] || d->ops[c].kind == OpKind::NoOp) continue;  // spliced further down itself
+        Op &o = d->ops[c];
+        const cb_node *progs[1] = {o.tree.data()};
+        const int32_t counts[1] = {(int32_t)o.tree.size()};
+        if (o.in.size() == 1) {
+            CB_TRY(cb_expr_compile(d->raw, o.dtype, CB_KERNEL_APPLY, progs, counts, 1, &o.expr));
+            o.kind = OpKind::Apply;
+            o.arg_ids = {o.out, o.in[0]};
+        } else {
+            CB_TRY(cb_expr_compile(d->raw, o.dtype, CB_KERNEL_BINARY, progs, counts, 1, &o.expr));
+            o.kind = OpKind::Apply2;
+            o.arg_ids = {o.in[0], o.in[1], o.out};
+        }
+        o.unary_hint = false;
+        o.hint.clear();
+        o.fused = true;
     }
     d->invalidate_replay();
     return CB_OK;

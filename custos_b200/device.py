@@ -264,6 +264,10 @@ class CUDA:
     def unary_fusing(self) -> None:
         N.call("cbm_unary_fusing", self.h)
 
+    def elementwise_fusing(self) -> None:
+        """Beyond the reference: binary ops fuse with neighbouring unary chains (at most two inputs per kernel)."""
+        N.call("cbm_elementwise_fusing", self.h)
+
     def cache_traces(self):
         cap = 1 << 16
         buf = (C.c_int64 * cap)()

@@ -364,6 +364,9 @@ int32_t cbm_replay_kernel_nodes(cbm_device *d, size_t *n);
 /* Graph: Optimize (src/modules/graph.rs:79-113) */
 int32_t cbm_optimize_mem_graph(cbm_device *d);
 int32_t cbm_unary_fusing(cbm_device *d);
+/* beyond the reference: splice producers that have a single reader into their consumer
+ * when the merged expression reads at most two buffers — binary ops fuse with neighbouring unary chains */
+int32_t cbm_elementwise_fusing(cbm_device *d);
 /* cache traces of the current graph: flattened as [cache_idx, k, use_0..use_{k-1}]* */
 int32_t cbm_cache_traces(cbm_device *d, int64_t *out, size_t cap, size_t *written);
 

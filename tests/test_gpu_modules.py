@@ -556,3 +556,90 @@ def test_sum_and_mean_through_the_module_layer():
         s = dev.sum(doubled)
         assert abs(float(s) - 2.0 * orc.sum_f64(orc.F32, x)) <= 1e-6 * 2.0 * orc.sum_f64(orc.F32, x)
         assert abs(float(dev.mean(buf)) - float(np.mean(x.astype(np.float64)))) < 1e-6
+
+
+# ------------------------------------------------------------------ element-wise fusing
+def test_elementwise_fusing_binary_with_unary_neighbours():
+    a_np, b_np = random_inputs(N.F32, 50_003, 80), random_inputs(N.F32, 50_003, 81)
+
+    def record(dev):
+        a, b = dev.buffer(a_np), dev.buffer(b_np)
+        s = dev.apply_fn(a, lambda x: x.mul(2.0).add(1.0))
+        c = dev.apply_fn(b, lambda x: x.abs())
+        t = dev.add(s, c)                      # (2a + 1) + |b|
+        u = dev.apply_fn(t, lambda x: x.neg().mul(0.5))
+        return a, b, s, c, t, u
+
+    with CUDA("Graph", "Lazy", "Base") as dev:
+        a, b, s, c, t, u = record(dev)
+        dev.run()
+        unfused = u.replace().read()
+        assert dev.ops_count() == 4
+    with CUDA("Graph", "Lazy", "Base") as dev:
+        a, b, s, c, t, u = record(dev)
+        dev.elementwise_fusing()
+        assert dev.op_hint_src(3) == "Fused: (-((((x * 2.0) + 1.0) + abs(y))) * 0.5)"
+        dev.alloc_later()
+        before = dev.raw.launches
+        dev.run()
+        assert dev.raw.launches - before == 1, "four recorded ops, two inputs: ONE kernel"
+        got = u.replace().read()
+        assert_bit_exact(got, unfused, "fused == unfused on the device")
+        want = orc.apply_fn(lambda x: x.neg().mul(0.5), orc.F32,
+                            orc.binary(0, orc.F32, orc.apply_fn(lambda x: x.mul(2.0).add(1.0), orc.F32, a_np),
+                                       orc.apply_fn(lambda x: x.abs(), orc.F32, b_np)))
+        assert_bit_exact(got, want, "fused expression vs oracle (exact ops only)")
+        assert t.replace().read().tolist()[:4] == [0.0] * 4  # fused-away intermediates are never written
+
+
+def test_elementwise_fusing_respects_readers_checkpoints_and_three_inputs():
+    x = random_inputs(N.F32, 10_001, 82)
+    with CUDA("Graph", "Lazy", "Base") as dev:
+        a, b, c = dev.buffer(x), dev.buffer(x * 2), dev.buffer(x * 3)
+        s = dev.apply_fn(a, lambda v: v.add(1.0))
+        p = dev.mul(s, b)            # s has two readers (p and q): must stay materialised
+        q = dev.add(s, c)
+        r = dev.add(p, q)            # p and q fold into r only while <= 2 inputs remain: they read s,b and s,c -> 3
+        k = dev.apply_fn(r, lambda v: v.mul(0.5)).checkpoint()
+        out = dev.apply_fn(k, lambda v: v.sub(1.0))   # k is checkpointed: not fused into out
+        dev.elementwise_fusing()
+        dev.run()
+        s_np = x + np.float32(1.0)
+        want_r = (s_np * (x * 2)) + (s_np + x * 3)
+        assert_bit_exact(s.replace().read(), s_np, "s is still computed")
+        assert_bit_exact(k.replace().read(), want_r * np.float32(0.5), "checkpointed buffer holds its value")
+        assert_bit_exact(out.replace().read(), want_r * np.float32(0.5) - np.float32(1.0), "result")
+
+
+def test_elementwise_fusing_collapses_the_20_op_sequence():
+    # the replay workload (10 unary pieces alternating with 10 binary adds against the same rhs): every
+    # intermediate has one reader and the expression only ever reads (a, b) -> a single kernel
+    n = 4096
+    x, y = random_inputs(N.F32, n, 70), random_inputs(N.F32, n, 71)
+    with CUDA("Graph", "Lazy", "Base") as dev:
+        a, b = dev.buffer(x), dev.buffer(y)
+        cur = a
+        for k in range(10):
+            cur = dev.apply_fn(cur, CHEAP8[k % 8])
+            cur = dev.add(cur, b)
+        dev.elementwise_fusing()
+        dev.alloc_later()
+        before = dev.raw.launches
+        dev.run()
+        assert dev.raw.launches - before == 1
+        want = x
+        for k in range(10):
+            want = orc.binary(0, orc.F32, orc.apply_fn(CHEAP8[k % 8], orc.F32, want), y)
+        assert_bit_exact(cur.replace().read(), want, "20 fused ops vs oracle")
+
+
+def test_elementwise_fusing_keeps_buffers_a_grad_function_needs():
+    with CUDA("Lazy", "Graph", "Autograd", "Base") as dev:
+        buf = dev.buffer(np.array([1., 2., 3., 4.], np.float32)).require_grad()
+        h = dev.unary_ew(buf, lambda x: x.sin(), lambda x: x.cos())
+        out = dev.unary_ew(h, lambda x: x.mul(2.0), lambda x: 2.0)
+        dev.elementwise_fusing()   # h is on the tape (backward reads it): nothing may be fused away
+        dev.run()
+        assert_ulp(h.replace().read(), np.sin(np.array([1., 2., 3., 4.], np.float32)), 2)
+        out.backward()
+        assert_ulp(buf.grad().read(), (2.0 * np.cos(np.array([1., 2., 3., 4.]))).astype(np.float32), 4)
