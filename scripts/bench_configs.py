@@ -121,6 +121,24 @@ def replay_config():
             dt = time.perf_counter() - t
             res[mode] = {"us_per_run": dt / reps * 1e6, "us_per_op": dt / reps * 1e6 / 20, "runs": reps}
     res["speedup"] = res["eager_launches"]["us_per_run"] / res["graph_replay"]["us_per_run"]
+    # beyond the reference: Graph + Lazy with element-wise fusing collapses the 20 ops into one kernel
+    with CUDA("Graph", "Lazy", "Base") as dev:
+        a, b = dev.buffer(x), dev.buffer(x)
+        cur = a
+        for k in range(10):
+            cur = dev.apply_fn(cur, CHAIN8[k % 8])
+            cur = dev.add(cur, b)
+        dev.elementwise_fusing()
+        dev.set_graph_replay(True)
+        dev.run()
+        dev.sync()
+        reps = 10000
+        t = time.perf_counter()
+        for _ in range(reps):
+            dev.run()
+        dev.sync()
+        dt = time.perf_counter() - t
+        res["elementwise_fused_graph_replay"] = {"us_per_run": dt / reps * 1e6, "kernels": dev.replay_kernel_nodes(), "runs": reps}
     return res
 
 
