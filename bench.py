@@ -306,7 +306,7 @@ def run_ours(args):
         "sustained": sustained,
     }
     if rank == 0 and world == 1:
-        out["cpu_baseline"] = cpu_baseline_single(1 << 25)
+        out["cpu_baseline"] = cpu_baseline_single(1 << 27)
     if rank == 0 and args.extra:
         out["extra"] = extra_workloads(dev, n)
     dev.host_free(h_in)
