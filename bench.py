@@ -109,6 +109,13 @@ class ClockSampler:
                 "reasons": sorted(name for bit, name in self.REASONS.items() if mask & bit),
                 "power_w_max": max(r[2] for r in rows), "samples": len(rows), "how": how}
 
+    def wait_ready(self, timeout: float = 5.0):
+        """Block until the poller has delivered its first sample (nvmlInit and the first query can take
+        longer than a whole 20 ms timed region on a fresh box)."""
+        t_end = time.time() + timeout
+        while self.ok and not self.samples and time.time() < t_end:
+            time.sleep(0.001)
+
     def stop(self):
         self._stop.set()
 
@@ -216,6 +223,7 @@ def run_ours(args):
 
     # ---------------------------------------------------------------- device-resident timing
     sampler = ClockSampler(local_rank)
+    sampler.wait_ready()
     for _ in range(args.warmup):
         dev.apply(chain, d_in, d_out, n)
     dev.sync()
