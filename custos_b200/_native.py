@@ -31,7 +31,7 @@ CB_OK = 0
 CB_ERR_INVALID_ARG, CB_ERR_ZERO_LENGTH, CB_ERR_NO_DEVICE, CB_ERR_UNSUPPORTED, CB_ERR_EXPR = 1, 2, 3, 4, 5
 CB_ERR_INVALID_LAZY_BUF, CB_ERR_MISSING_CACHE_TRACES, CB_ERR_GRAPH_OPTIMIZATION = 6, 7, 8
 CB_ERR_SHAPE, CB_ERR_STATE = 9, 10
-F32, F64, F16, I32, I64, U32, U8 = range(7)
+F32, F64, F16, I32, I64, U32, U8, BF16, I8, I16, U16, U64, BOOL = range(13)
 KERNEL_APPLY, KERNEL_UNARY_GRAD, KERNEL_BINARY = 0, 1, 2
 BIN_ADD, BIN_MUL, BIN_SUB, BIN_DIV = 0, 1, 2, 3
 CBM_BASE, CBM_CACHED, CBM_LAZY, CBM_GRAPH, CBM_AUTOGRAD = 0, 1, 2, 4, 8

@@ -220,6 +220,7 @@ extern "C" int32_t cb_comm_destroy(cb_comm *c)
 static int32_t comm_reduce(cb_comm *c, int32_t dtype, uint64_t in, size_t n_local, uint64_t out, size_t divisor)
 {
     CB_CHECK_ARG(c && cb::valid_dtype(dtype) && out, "bad argument");
+    if (dtype == CB_BOOL) return cb::fail(CB_ERR_UNSUPPORTED, "bool has no arithmetic in the reference (storage only)");
     cb_device *dev = c->dev;
     CB_TRY(dev->use());
     if (c->p2p) {
@@ -246,7 +247,7 @@ static int32_t comm_reduce(cb_comm *c, int32_t dtype, uint64_t in, size_t n_loca
     } else {
         CB_TRY(cb_sum(dev, dtype, in, n_local, reinterpret_cast<uint64_t>(c->local)));
     }
-    const int nccl_type = (dtype == CB_F32 || dtype == CB_F16) ? ncclFloat32 : (dtype == CB_F64 ? ncclFloat64 : ncclInt64);
+    const int nccl_type = (dtype == CB_F32 || cb::is_half_dtype(dtype)) ? ncclFloat32 : (dtype == CB_F64 ? ncclFloat64 : ncclInt64);
     int r = nccl().AllGather(c->local, c->gathered, 1, nccl_type, c->comm, dev->stream);
     if (r != ncclSuccess) return nccl_fail(r, "ncclAllGather");
     cudaError_t e = cb::launch_fold_ranks(dev->ctx(), dtype, c->gathered, c->n_ranks, reinterpret_cast<void *>(out), divisor);

@@ -25,8 +25,9 @@ inline int32_t fail(int32_t code, const char *fmt, ...)
     return code;
 }
 
-inline bool is_float_dtype(int32_t dt) { return dt == CB_F32 || dt == CB_F64 || dt == CB_F16; }
-inline bool is_signed_int_dtype(int32_t dt) { return dt == CB_I32 || dt == CB_I64; }
+inline bool is_float_dtype(int32_t dt) { return dt == CB_F32 || dt == CB_F64 || dt == CB_F16 || dt == CB_BF16; }
+inline bool is_half_dtype(int32_t dt) { return dt == CB_F16 || dt == CB_BF16; }  // 16-bit storage, f32 arithmetic
+inline bool is_signed_int_dtype(int32_t dt) { return dt == CB_I32 || dt == CB_I64 || dt == CB_I8 || dt == CB_I16; }
 inline bool valid_dtype(int32_t dt) { return dt >= 0 && dt < CB_DTYPE_COUNT; }
 size_t dtype_size(int32_t dt);
 const char *dtype_name(int32_t dt);

@@ -48,6 +48,7 @@ struct Tunables {
     int waves = 16;  // CB_WAVES: grid cap = SMs x resident blocks x waves; >1 lets the hardware rebalance
                      // SMs that run slower (a single static wave left ~10% on the table, profiles/r1_tuning.md)
     int pair = 1;  // CB_PAIR: f32 chains evaluate two elements per thread on the packed f32x2 pipe
+    int h_native = 1;  // CB_H_NATIVE: f16 add / sub / mul as single HFMA2s on packed halves
     std::string ld_mod = ".cs";
     std::string st_mod = ".cs";
     std::string dump_dir;  // CB_DUMP_DIR: write generated sources and cubins here

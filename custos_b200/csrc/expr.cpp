@@ -35,6 +35,7 @@ static const char *op_name(int32_t op)
 static bool op_supported(int32_t dtype, int32_t op)
 {
     if (is_float_dtype(dtype)) return true;
+    if (dtype == CB_BOOL) return false;  // bool is a CDatatype but not a Number: storage only
     switch (op) {
     case CB_OP_X: case CB_OP_Y: case CB_OP_CONST: case CB_OP_ADD: case CB_OP_MUL: case CB_OP_SUB:
     case CB_OP_DIV: case CB_OP_GEQ: case CB_OP_LEQ: case CB_OP_EQ:
@@ -62,11 +63,10 @@ int32_t expr_validate(int32_t dtype, int32_t kind, const cb_node *nodes, int32_t
             if (op_is_binary(c.op) && (c.b < 0 || c.b >= i))
                 return fail(CB_ERR_EXPR, "node %d: operand b=%d out of order", i, c.b);
         }
-        if (c.op == CB_OP_CONST && dtype == CB_F16) {
-            const float f = (float)c.fimm;
-            if (std::isfinite(c.fimm) && (double)host_f16_to_f32(host_f32_to_f16(f)) != c.fimm)
-                return fail(CB_ERR_EXPR, "node %d: literal %.17g is not representable in f16 (round it first)", i,
-                            c.fimm);
+        if (c.op == CB_OP_CONST && is_half_dtype(dtype)) {
+            if (std::isfinite(c.fimm) && (double)host_half_to_f32(dtype, host_f32_to_half(dtype, (float)c.fimm)) != c.fimm)
+                return fail(CB_ERR_EXPR, "node %d: literal %.17g is not representable in %s (round it first)", i,
+                            c.fimm, dtype_name(dtype));
         }
         if (c.op == CB_OP_CONST && dtype == CB_F32 && std::isfinite(c.fimm) && (double)(float)c.fimm != c.fimm)
             return fail(CB_ERR_EXPR, "node %d: literal %.17g is not representable in f32 (round it first)", i, c.fimm);
@@ -118,6 +118,30 @@ float host_f16_to_f32(uint16_t h)
     return s ? -r : r;
 }
 
+// ------------------------------------------------------------------ bfloat16 (host)
+// half::bf16::from_f32: NaN keeps its top payload bits with the quiet bit forced, everything else is
+// round-to-nearest-even on the upper 16 bits (overflow carries into infinity by itself).
+uint16_t host_f32_to_bf16(float v)
+{
+    uint32_t u;
+    std::memcpy(&u, &v, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x0040u);
+    const uint32_t round_bit = 0x8000u;
+    if ((u & round_bit) && (u & (3u * round_bit - 1u))) return (uint16_t)((u >> 16) + 1u);
+    return (uint16_t)(u >> 16);
+}
+
+float host_bf16_to_f32(uint16_t h)
+{
+    const uint32_t u = (uint32_t)h << 16;
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+
+uint16_t host_f32_to_half(int32_t dtype, float v) { return dtype == CB_BF16 ? host_f32_to_bf16(v) : host_f32_to_f16(v); }
+float host_half_to_f32(int32_t dtype, uint16_t h) { return dtype == CB_BF16 ? host_bf16_to_f32(h) : host_f16_to_f32(h); }
+
 // ------------------------------------------------------------ Rust `{:?}` for numbers
 // core::fmt::float: shortest digits that round-trip; decimal with at least one
 // fractional digit when 1e-4 <= |v| < 1e16 (or v == 0), exponential ("1e16", "1.5e-7")
@@ -167,9 +191,14 @@ std::string rust_debug_literal(int32_t dtype, const cb_node &c)
     switch (dtype) {
     case CB_F32: return rust_debug_float((double)(float)c.fimm, true);
     case CB_F64: return rust_debug_float(c.fimm, false);
-    case CB_F16: return rust_debug_float((double)host_f16_to_f32(host_f32_to_f16((float)c.fimm)), true);  // half: Debug via f32
+    case CB_F16: case CB_BF16:  // half: Debug via f32
+        return rust_debug_float((double)host_half_to_f32(dtype, host_f32_to_half(dtype, (float)c.fimm)), true);
     case CB_U32: return std::to_string((uint32_t)c.iimm);
     case CB_U8: return std::to_string((unsigned)(uint8_t)c.iimm);
+    case CB_U16: return std::to_string((unsigned)(uint16_t)c.iimm);
+    case CB_U64: return std::to_string((unsigned long long)c.iimm);
+    case CB_I8: return std::to_string((int)(int8_t)c.iimm);
+    case CB_I16: return std::to_string((int)(int16_t)c.iimm);
     case CB_I32: return std::to_string((int32_t)c.iimm);
     default: return std::to_string((long long)c.iimm);
     }
@@ -230,7 +259,11 @@ static std::string cuda_literal(int32_t dtype, const cb_node &c)
         std::memcpy(&u, &c.fimm, 8);
         std::snprintf(buf, sizeof buf, "__longlong_as_double((long long)0x%016llxULL)", (unsigned long long)u);
     } break;
-    case CB_F16: std::snprintf(buf, sizeof buf, "((T)0x%04xu)", (unsigned)host_f32_to_f16((float)c.fimm)); break;
+    case CB_F16: case CB_BF16:
+        std::snprintf(buf, sizeof buf, "((T)0x%04xu)", (unsigned)host_f32_to_half(dtype, (float)c.fimm));
+        break;
+    case CB_I8: std::snprintf(buf, sizeof buf, "((T)0x%02xu)", (unsigned)(uint8_t)c.iimm); break;
+    case CB_I16: case CB_U16: std::snprintf(buf, sizeof buf, "((T)0x%04xu)", (unsigned)(uint16_t)c.iimm); break;
     case CB_I32: std::snprintf(buf, sizeof buf, "((T)0x%08xu)", (unsigned)(uint32_t)(int32_t)c.iimm); break;
     case CB_U32: std::snprintf(buf, sizeof buf, "((T)0x%08xu)", (unsigned)(uint32_t)c.iimm); break;
     case CB_U8: std::snprintf(buf, sizeof buf, "((T)0x%02xu)", (unsigned)(uint8_t)c.iimm); break;
@@ -316,11 +349,11 @@ std::string expr_cuda_function(int32_t dtype, const cb_node *const *progs, const
         }
         s += "    return x;\n}\n#endif\n";
     }
-    if (dtype == CB_F16) {
-        // two binary16 elements per 32-bit word (skeleton.cuh: cbw_*); ops with a literal operand take the
+    if (is_half_dtype(dtype)) {
+        // two binary16 / bfloat16 elements per 32-bit word (skeleton.cuh: cbw_*); ops with a literal operand take the
         // mixed-precision forms that need no unpack
-        auto f32_bits_of = [](const cb_node &c, bool negate) {
-            float f = host_f16_to_f32(host_f32_to_f16((float)c.fimm));
+        auto f32_bits_of = [dtype](const cb_node &c, bool negate) {
+            float f = host_half_to_f32(dtype, host_f32_to_half(dtype, (float)c.fimm));
             if (negate) f = -f;
             uint32_t u;
             std::memcpy(&u, &f, 4);
@@ -328,9 +361,9 @@ std::string expr_cuda_function(int32_t dtype, const cb_node *const *progs, const
             std::snprintf(buf, sizeof buf, "__uint_as_float(0x%08xu)", u);
             return std::string(buf);
         };
-        auto half_bits_of = [](const cb_node &c) {
+        auto half_bits_of = [dtype](const cb_node &c) {
             char buf[32];
-            std::snprintf(buf, sizeof buf, "(T)0x%04xu", (unsigned)host_f32_to_f16((float)c.fimm));
+            std::snprintf(buf, sizeof buf, "(T)0x%04xu", (unsigned)host_f32_to_half(dtype, (float)c.fimm));
             return std::string(buf);
         };
         s += "#if CB_PAIR\n__device__ __forceinline__ cb_w cb_fnw(cb_w x, cb_w y, bool &redo)\n{\n";
@@ -347,7 +380,7 @@ std::string expr_cuda_function(int32_t dtype, const cb_node *const *progs, const
                 else if (c.op == CB_OP_Y) rhs = "y";
                 else if (c.op == CB_OP_CONST) {
                     char buf[32];
-                    std::snprintf(buf, sizeof buf, "cbw_lit(0x%04xu)", (unsigned)host_f32_to_f16((float)c.fimm));
+                    std::snprintf(buf, sizeof buf, "cbw_lit(0x%04xu)", (unsigned)host_f32_to_half(dtype, (float)c.fimm));
                     rhs = buf;
                 } else if (c.op == CB_OP_ADD && b_const) rhs = "cbw_add_c(" + ta + ", " + f32_bits_of(nd[c.b], false) + ")";
                 else if (c.op == CB_OP_ADD && a_const) rhs = "cbw_add_c(" + tb + ", " + f32_bits_of(nd[c.a], false) + ")";

@@ -38,5 +38,9 @@ uint64_t chain_hash(int32_t dtype, int32_t kind, const cb_node *const *progs, co
 // IEEE binary16 <-> binary32, round to nearest even (host side, for f16 literals)
 uint16_t host_f32_to_f16(float v);
 float host_f16_to_f32(uint16_t h);
+uint16_t host_f32_to_bf16(float v);
+float host_bf16_to_f32(uint16_t h);
+uint16_t host_f32_to_half(int32_t dtype, float v);  // dtype CB_F16 or CB_BF16
+float host_half_to_f32(int32_t dtype, uint16_t h);
 
 }  // namespace cb

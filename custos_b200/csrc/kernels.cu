@@ -43,7 +43,7 @@ union Pack {
 };
 
 // ------------------------------------------------------------------ element arithmetic
-// f16 is carried as its bit pattern; arithmetic is f32 with one RNE back (half crate).
+// f16 / bf16 are carried as their bit patterns; arithmetic is f32 with one RNE back (half crate).
 struct half_bits {
     unsigned short b;
 };
@@ -57,6 +57,18 @@ __device__ __forceinline__ unsigned short f2h(float f)
 {
     unsigned short h;
     asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(f));
+    return h;
+}
+
+// bf16: the upper half of an f32; half::bf16 arithmetic is f32 with one RNE back, like f16
+struct bf16_bits {
+    unsigned short b;
+};
+__device__ __forceinline__ float b2f(unsigned short h) { return __uint_as_float((unsigned int)h << 16); }
+__device__ __forceinline__ unsigned short f2b(float f)
+{
+    unsigned short h;
+    asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(h) : "f"(f));
     return h;
 }
 
@@ -89,16 +101,24 @@ struct BinOp<half_bits, OP> {
         return half_bits{f2h(BinOp<float, OP>::apply(h2f(a.b), h2f(b.b)))};
     }
 };
+template <int OP>
+struct BinOp<bf16_bits, OP> {
+    static __device__ __forceinline__ bf16_bits apply(bf16_bits a, bf16_bits b)
+    {
+        return bf16_bits{f2b(BinOp<float, OP>::apply(b2f(a.b), b2f(b.b)))};
+    }
+};
 template <typename T, int OP>
 struct BinOp {  // integers: wrapping, x / 0 = 0
-    typedef typename std::conditional<sizeof(T) == 8, unsigned long long,
-                                      typename std::conditional<sizeof(T) == 4, unsigned int, unsigned char>::type>::type U;
+    typedef typename std::make_unsigned<T>::type U;
     static __device__ __forceinline__ T apply(T a, T b)
     {
         if (OP == CB_BIN_ADD) return (T)((U)a + (U)b);
         if (OP == CB_BIN_MUL) return (T)((U)a * (U)b);
         if (OP == CB_BIN_SUB) return (T)((U)a - (U)b);
-        return b == (T)0 ? (T)0 : (T)(a / b);
+        if (b == (T)0) return (T)0;
+        if ((T)-1 < (T)0 && b == (T)-1) return (T)((U)0 - (U)a);  // MIN / -1 wraps to MIN (the reference panics)
+        return (T)(a / b);
     }
 };
 
@@ -223,6 +243,8 @@ template <typename T, typename ACC>
 __device__ __forceinline__ ACC to_acc(T v) { return (ACC)v; }
 template <>
 __device__ __forceinline__ float to_acc<half_bits, float>(half_bits v) { return h2f(v.b); }
+template <>
+__device__ __forceinline__ float to_acc<bf16_bits, float>(bf16_bits v) { return b2f(v.b); }
 
 template <typename ACC>
 __device__ __forceinline__ ACC shfl_xor(ACC v, int off) { return __shfl_xor_sync(0xffffffffu, v, off); }
@@ -459,6 +481,11 @@ cudaError_t launch_binary(const LaunchCtx &ctx, int dtype, int op, const void *l
     case CB_I64: return launch_binary_op<long long>(ctx, op, lhs, rhs, out, n);
     case CB_U32: return launch_binary_op<unsigned int>(ctx, op, lhs, rhs, out, n);
     case CB_U8: return launch_binary_op<unsigned char>(ctx, op, lhs, rhs, out, n);
+    case CB_BF16: return launch_binary_op<bf16_bits>(ctx, op, lhs, rhs, out, n);
+    case CB_I8: return launch_binary_op<signed char>(ctx, op, lhs, rhs, out, n);
+    case CB_I16: return launch_binary_op<short>(ctx, op, lhs, rhs, out, n);
+    case CB_U16: return launch_binary_op<unsigned short>(ctx, op, lhs, rhs, out, n);
+    case CB_U64: return launch_binary_op<unsigned long long>(ctx, op, lhs, rhs, out, n);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -539,7 +566,7 @@ int launch_copy_count(const void *dst, const void *src, size_t bytes)
 
 void sum_plan(int dtype, size_t n, int *blocks, size_t *chunk, int *threads, int *vec, int *threads2)
 {
-    static const int sizes[CB_DTYPE_COUNT] = {4, 8, 2, 4, 8, 4, 1};
+    static const int sizes[CB_DTYPE_COUNT] = {4, 8, 2, 4, 8, 4, 1, 2, 1, 2, 2, 8, 1};
     const int v = 16 / sizes[dtype];
     const size_t unit = (size_t)kThreads * (size_t)v;
     size_t b = (n + unit - 1) / unit;
@@ -571,6 +598,11 @@ cudaError_t launch_sum(const LaunchCtx &ctx, int dtype, const void *in, size_t n
     case CB_I64: return launch_sum_t<long long, long long>(ctx, in, n, blocks, chunk, partials, out, divisor);
     case CB_U32: return launch_sum_t<unsigned int, long long>(ctx, in, n, blocks, chunk, partials, out, divisor);
     case CB_U8: return launch_sum_t<unsigned char, long long>(ctx, in, n, blocks, chunk, partials, out, divisor);
+    case CB_BF16: return launch_sum_t<bf16_bits, float>(ctx, in, n, blocks, chunk, partials, out, divisor);
+    case CB_I8: return launch_sum_t<signed char, long long>(ctx, in, n, blocks, chunk, partials, out, divisor);
+    case CB_I16: return launch_sum_t<short, long long>(ctx, in, n, blocks, chunk, partials, out, divisor);
+    case CB_U16: return launch_sum_t<unsigned short, long long>(ctx, in, n, blocks, chunk, partials, out, divisor);
+    case CB_U64: return launch_sum_t<unsigned long long, long long>(ctx, in, n, blocks, chunk, partials, out, divisor);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -590,6 +622,11 @@ cudaError_t launch_sum_exchange(const LaunchCtx &ctx, int dtype, const void *in,
     case CB_I64: return launch_sum_xchg_t<long long, long long>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
     case CB_U32: return launch_sum_xchg_t<unsigned int, long long>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
     case CB_U8: return launch_sum_xchg_t<unsigned char, long long>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
+    case CB_BF16: return launch_sum_xchg_t<bf16_bits, float>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
+    case CB_I8: return launch_sum_xchg_t<signed char, long long>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
+    case CB_I16: return launch_sum_xchg_t<short, long long>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
+    case CB_U16: return launch_sum_xchg_t<unsigned short, long long>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
+    case CB_U64: return launch_sum_xchg_t<unsigned long long, long long>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -598,7 +635,7 @@ cudaError_t launch_fold_ranks(const LaunchCtx &ctx, int dtype, const void *gathe
 {
     (void)cudaGetLastError();  // a stale error of an earlier, unchecked call must not be blamed on this launch
     switch (dtype) {
-    case CB_F32: case CB_F16:
+    case CB_F32: case CB_F16: case CB_BF16:
         fold_ranks_kernel<float><<<1, 32, 0, ctx.stream>>>((const float *)gathered, n_ranks, (float *)out, divisor);
         break;
     case CB_F64:

@@ -20,10 +20,26 @@ OP = {name: i for i, name in enumerate(OPS)}
 BINARY = {"add", "mul", "sub", "div", "pow", "min", "max", "geq", "leq", "eq"}
 UNARY = {"sin", "cos", "tan", "tanh", "exp", "ln", "abs", "neg", "identity"}
 
+# numpy has no bfloat16: a bf16 buffer travels as its uint16 bit patterns (bf16_from_f32 / bf16_to_f32 below)
 NP_DTYPE = {N.F32: np.float32, N.F64: np.float64, N.F16: np.float16, N.I32: np.int32, N.I64: np.int64,
-            N.U32: np.uint32, N.U8: np.uint8}
-DTYPE_OF_NP = {np.dtype(v): k for k, v in NP_DTYPE.items()}
-FLOAT_DTYPES = (N.F32, N.F64, N.F16)
+            N.U32: np.uint32, N.U8: np.uint8, N.BF16: np.uint16, N.I8: np.int8, N.I16: np.int16,
+            N.U16: np.uint16, N.U64: np.uint64, N.BOOL: np.bool_}
+DTYPE_OF_NP = {np.dtype(v): k for k, v in NP_DTYPE.items() if k != N.BF16}
+FLOAT_DTYPES = (N.F32, N.F64, N.F16, N.BF16)
+
+
+def bf16_from_f32(a) -> np.ndarray:
+    """f32 -> bf16 bit patterns, round to nearest even; NaN keeps its top payload bits plus the quiet bit
+    (what `half::bf16::from_f32` does)."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    nan = (u & 0x7fffffff) > 0x7f800000
+    lower, q = u & 0xffff, u >> 16
+    q = q + ((lower > 0x8000) | ((lower == 0x8000) & ((q & 1) == 1)))
+    return np.where(nan, (u >> 16) | 0x40, q).astype(np.uint16)
+
+
+def bf16_to_f32(bits) -> np.ndarray:
+    return (np.ascontiguousarray(bits, dtype=np.uint16).astype(np.uint32) << 16).view(np.float32)
 
 
 def dtype_code(dtype) -> int:
@@ -110,8 +126,12 @@ def flatten(f: Callable | Combiner, dtype, n_args: int = 1):
     for i, (node, a, b) in enumerate(order):
         arr[i].op, arr[i].a, arr[i].b = OP[node.op], a, b
         if node.op == "const":
-            if dt in FLOAT_DTYPES:
+            if dt == N.BF16:
+                arr[i].fimm = float(bf16_to_f32(bf16_from_f32([node.value]))[0])
+            elif dt in FLOAT_DTYPES:
                 arr[i].fimm = float(NP_DTYPE[dt](node.value))
+            elif dt == N.U64:
+                arr[i].iimm = int(np.uint64(node.value).astype(np.int64))
             else:
                 arr[i].iimm = int(NP_DTYPE[dt](node.value))
     return arr, len(order)

@@ -159,7 +159,7 @@ class RawDevice:
 
     def fill(self, dtype, dptr: int, n: int, value):
         dt = dtype_code(dtype)
-        isf = dt in (N.F32, N.F64, N.F16)
+        isf = dt in (N.F32, N.F64, N.F16, N.BF16)
         N.call("cb_fill", self.h, dt, dptr, n, float(value) if isf else 0.0, 0 if isf else int(value))
 
     def copy(self, dtype, dst: int, dst_off: int, src: int, src_off: int, n: int):
@@ -194,7 +194,7 @@ class RawDevice:
     @staticmethod
     def acc_dtype(dtype):
         dt = dtype_code(dtype)
-        return np.float32 if dt in (N.F32, N.F16) else (np.float64 if dt == N.F64 else np.int64)
+        return np.float32 if dt in (N.F32, N.F16, N.BF16) else (np.float64 if dt == N.F64 else np.int64)
 
     def sum(self, dtype, dptr: int, n: int):
         out = np.zeros(1, dtype=self.acc_dtype(dtype))

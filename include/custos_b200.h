@@ -60,8 +60,8 @@ const char *cb_last_error(void);
 int32_t cb_abi_version(void);
 
 /* ------------------------------------------------------------------ dtypes */
-/* CDatatype (src/devices/cdatatype.rs:3-62).  bf16 is deliberately absent: the
- * reference maps it to "half", which is wrong (cdatatype.rs:58-62). */
+/* Every CDatatype (src/devices/cdatatype.rs:3-62).  Values 0..6 are stable since ABI 1; 7..12
+ * were appended later, which is why the list is not sorted by width. */
 typedef enum cb_dtype {
     CB_F32 = 0,
     CB_F64 = 1,
@@ -72,7 +72,16 @@ typedef enum cb_dtype {
     CB_I64 = 4,
     CB_U32 = 5,
     CB_U8  = 6,
-    CB_DTYPE_COUNT = 7
+    CB_BF16 = 7,  /* bfloat16 storage, same per-op f32 arithmetic + RNE (number.rs:611-676).  The
+                     reference names it "half" in kernel source (cdatatype.rs:58-62, its own TODO
+                     says that is wrong); this backend follows the CPU device, i.e. real bf16 */
+    CB_I8  = 8,
+    CB_I16 = 9,
+    CB_U16 = 10,
+    CB_U64 = 11,
+    CB_BOOL = 12, /* one byte per element; storage only (alloc / clear / copy / read / write):
+                     bool has no Number impl, so no expression can be built over it */
+    CB_DTYPE_COUNT = 13
 } cb_dtype;
 
 size_t cb_dtype_size(int32_t dtype);

@@ -23,6 +23,12 @@ size_t orc_dtype_size(int dtype)
     case ORC_I64: return 8;
     case ORC_U32: return 4;
     case ORC_U8: return 1;
+    case ORC_BF16: return 2;
+    case ORC_I8: return 1;
+    case ORC_I16: return 2;
+    case ORC_U16: return 2;
+    case ORC_U64: return 8;
+    case ORC_BOOL: return 1;
     default: return 0;
     }
 }
@@ -91,6 +97,29 @@ float orc_f16_to_f32(uint16_t h)
     return out;
 }
 
+/* ------------------------------------------------------------------ bfloat16
+ * half::bf16::from_f32 / to_f32: the upper 16 bits of the f32, round to nearest even on the
+ * dropped half; a NaN keeps its top payload bits and gets the quiet bit (0x0040). */
+uint16_t orc_f32_to_bf16(float v)
+{
+    uint32_t bits;
+    memcpy(&bits, &v, 4);
+    if ((bits & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((bits >> 16) | 0x0040u);
+    const uint32_t lower = bits & 0xffffu;
+    uint32_t q = bits >> 16;
+    if (lower > 0x8000u || (lower == 0x8000u && (q & 1u))) q += 1; /* may carry into the exponent / inf */
+    return (uint16_t)q;
+}
+
+float orc_bf16_to_f32(uint16_t h)
+{
+    uint32_t bits = (uint32_t)h << 16;
+    if ((h & 0x7fffu) > 0x7f80u) bits |= 0x00400000u;
+    float out;
+    memcpy(&out, &bits, 4);
+    return out;
+}
+
 /* ------------------------------------------------------------- program check */
 static int check_prog(const orc_node *nd, int n)
 {
@@ -153,47 +182,54 @@ static int check_prog(const orc_node *nd, int n)
 DEFINE_FLOAT_EVAL(eval_f32, float, expf, logf, sinf, cosf, tanf, tanhf, powf, fabsf)
 DEFINE_FLOAT_EVAL(eval_f64, double, exp, log, sin, cos, tan, tanh, pow, fabs)
 
-/* --------------------------------------------------- Eval for f16
- * Float for half::f16 (src/number.rs:543-608): every function goes to f32 and back
- * (`Self::from_f32(self.to_f32().exp())`), `tan` calls cos (line 575-577); + - * /
- * are `half`'s operators (f32 arithmetic, rounded back after each op). */
-static uint16_t eval_f16(const orc_node *nd, int n, uint16_t x, uint16_t y)
+/* --------------------------------------------------- Eval for f16 / bf16
+ * Float for half::f16 (src/number.rs:543-608) and half::bf16 (:611-676): every function goes
+ * to f32 and back (`Self::from_f32(self.to_f32().exp())`), `tan` calls cos (lines 575-577 and
+ * 643-645); + - * / are `half`'s operators (f32 arithmetic, rounded back after each op).
+ * Number::max for f16 forwards to half's inherent f16::max (number.rs:537-539), which keeps
+ * `self` unless `other > self`; bf16 (number.rs:515-531) and both mins use the trait defaults
+ * `if self > rhs { self } else { rhs }` / `if self < rhs { self } else { rhs }` (:202-209). */
+static uint16_t eval_half(int bf, const orc_node *nd, int n, uint16_t x, uint16_t y)
 {
+#define TO_F32(h) (bf ? orc_bf16_to_f32(h) : orc_f16_to_f32(h))
+#define FROM_F32(f) (bf ? orc_f32_to_bf16(f) : orc_f32_to_f16(f))
     uint16_t v[ORC_MAX_NODES];
     for (int i = 0; i < n; i++) {
         const orc_node *c = &nd[i];
         const uint16_t ha = c->a >= 0 ? v[c->a] : 0;
         const uint16_t hb = c->b >= 0 ? v[c->b] : 0;
-        const float a = orc_f16_to_f32(ha), b = orc_f16_to_f32(hb);
+        const float a = TO_F32(ha), b = TO_F32(hb);
         uint16_t r;
         switch (c->op) {
         case ORC_OP_X: r = x; break;
         case ORC_OP_Y: r = y; break;
-        case ORC_OP_CONST: r = orc_f32_to_f16((float)c->fimm); break;
-        case ORC_OP_ADD: r = orc_f32_to_f16(a + b); break;
-        case ORC_OP_MUL: r = orc_f32_to_f16(a * b); break;
-        case ORC_OP_SUB: r = orc_f32_to_f16(a - b); break;
-        case ORC_OP_DIV: r = orc_f32_to_f16(a / b); break;
-        case ORC_OP_POW: r = orc_f32_to_f16(powf(a, b)); break;
+        case ORC_OP_CONST: r = FROM_F32((float)c->fimm); break;
+        case ORC_OP_ADD: r = FROM_F32(a + b); break;
+        case ORC_OP_MUL: r = FROM_F32(a * b); break;
+        case ORC_OP_SUB: r = FROM_F32(a - b); break;
+        case ORC_OP_DIV: r = FROM_F32(a / b); break;
+        case ORC_OP_POW: r = FROM_F32(powf(a, b)); break;
         case ORC_OP_MIN: r = (a < b) ? ha : hb; break;
-        case ORC_OP_MAX: r = (a > b) ? ha : hb; break;
-        case ORC_OP_SIN: r = orc_f32_to_f16(sinf(a)); break;
-        case ORC_OP_COS: r = orc_f32_to_f16(cosf(a)); break;
-        case ORC_OP_TAN: r = orc_f32_to_f16(cosf(a)); break; /* sic: number.rs:575-577 */
-        case ORC_OP_TANH: r = orc_f32_to_f16(tanhf(a)); break;
-        case ORC_OP_EXP: r = orc_f32_to_f16(expf(a)); break;
-        case ORC_OP_LN: r = orc_f32_to_f16(logf(a)); break;
-        case ORC_OP_ABS: r = orc_f32_to_f16(fabsf(a)); break;
+        case ORC_OP_MAX: r = bf ? ((a > b) ? ha : hb) : ((b > a) ? hb : ha); break;
+        case ORC_OP_SIN: r = FROM_F32(sinf(a)); break;
+        case ORC_OP_COS: r = FROM_F32(cosf(a)); break;
+        case ORC_OP_TAN: r = FROM_F32(cosf(a)); break; /* sic */
+        case ORC_OP_TANH: r = FROM_F32(tanhf(a)); break;
+        case ORC_OP_EXP: r = FROM_F32(expf(a)); break;
+        case ORC_OP_LN: r = FROM_F32(logf(a)); break;
+        case ORC_OP_ABS: r = FROM_F32(fabsf(a)); break;
         case ORC_OP_NEG: r = (uint16_t)(ha ^ 0x8000u); break; /* half: Neg flips the sign bit */
         case ORC_OP_IDENTITY: r = ha; break;
-        case ORC_OP_GEQ: r = orc_f32_to_f16(a >= b ? 1.0f : 0.0f); break;
-        case ORC_OP_LEQ: r = orc_f32_to_f16(a <= b ? 1.0f : 0.0f); break;
-        default: r = orc_f32_to_f16(a <= b ? 1.0f : 0.0f); break;
+        case ORC_OP_GEQ: r = FROM_F32(a >= b ? 1.0f : 0.0f); break;
+        case ORC_OP_LEQ: r = FROM_F32(a <= b ? 1.0f : 0.0f); break;
+        default: r = FROM_F32(a <= b ? 1.0f : 0.0f); break;
         }
         v[i] = r;
     }
     return v[n - 1];
 }
+static uint16_t eval_f16(const orc_node *nd, int n, uint16_t x, uint16_t y) { return eval_half(0, nd, n, x, y); }
+static uint16_t eval_bf16(const orc_node *nd, int n, uint16_t x, uint16_t y) { return eval_half(1, nd, n, x, y); }
 
 /* --------------------------------------------------- Eval for integers
  * Only Add/Mul/Sub/Div/Neg(signed)/GEq/LEq/Eq have integer impls; the Float-bounded
@@ -209,7 +245,7 @@ static int int_op_supported(int op, int is_signed)
     }
 }
 
-#define DEFINE_INT_EVAL(NAME, T, UT)                                                               \
+#define DEFINE_INT_EVAL(NAME, T, UT, SIGNED)                                                               \
     static T NAME(const orc_node *nd, int n, T x, T y)                                             \
     {                                                                                              \
         T v[ORC_MAX_NODES];                                                                        \
@@ -225,7 +261,9 @@ static int int_op_supported(int op, int is_signed)
             case ORC_OP_ADD: r = (T)((UT)a + (UT)b); break;                                        \
             case ORC_OP_MUL: r = (T)((UT)a * (UT)b); break;                                        \
             case ORC_OP_SUB: r = (T)((UT)a - (UT)b); break;                                        \
-            case ORC_OP_DIV: r = (b == 0) ? (T)0 : (T)(a / b); break;                              \
+            case ORC_OP_DIV: /* x / 0 and MIN / -1 panic in Rust; defined here as 0 and MIN */     \
+                r = (b == 0) ? (T)0 : ((SIGNED && b == (T)-1) ? (T)((UT)0 - (UT)a) : (T)(a / b)); \
+                break;                                                                             \
             case ORC_OP_NEG: r = (T)((UT)0 - (UT)a); break;                                        \
             case ORC_OP_GEQ: r = (T)(a >= b); break;                                               \
             case ORC_OP_LEQ: r = (T)(a <= b); break;                                               \
@@ -236,18 +274,23 @@ static int int_op_supported(int op, int is_signed)
         return v[n - 1];                                                                           \
     }
 
-DEFINE_INT_EVAL(eval_i32, int32_t, uint32_t)
-DEFINE_INT_EVAL(eval_i64, int64_t, uint64_t)
-DEFINE_INT_EVAL(eval_u32, uint32_t, uint32_t)
-DEFINE_INT_EVAL(eval_u8, uint8_t, uint8_t)
+DEFINE_INT_EVAL(eval_i32, int32_t, uint32_t, 1)
+DEFINE_INT_EVAL(eval_i64, int64_t, uint64_t, 1)
+DEFINE_INT_EVAL(eval_u32, uint32_t, uint32_t, 0)
+DEFINE_INT_EVAL(eval_u8, uint8_t, uint8_t, 0)
+DEFINE_INT_EVAL(eval_i8, int8_t, uint8_t, 1)
+DEFINE_INT_EVAL(eval_i16, int16_t, uint16_t, 1)
+DEFINE_INT_EVAL(eval_u16, uint16_t, uint16_t, 0)
+DEFINE_INT_EVAL(eval_u64, uint64_t, uint64_t, 0)
 
 static int check_dtype_prog(int dtype, const orc_node *nd, int n)
 {
     int rc = check_prog(nd, n);
     if (rc) return rc;
-    if (dtype == ORC_F32 || dtype == ORC_F64 || dtype == ORC_F16) return ORC_OK;
-    if (dtype < 0 || dtype > ORC_U8) return ORC_ERR_ARG;
-    const int is_signed = (dtype == ORC_I32 || dtype == ORC_I64);
+    if (dtype == ORC_F32 || dtype == ORC_F64 || dtype == ORC_F16 || dtype == ORC_BF16) return ORC_OK;
+    if (dtype < 0 || dtype >= ORC_DTYPE_COUNT) return ORC_ERR_ARG;
+    if (dtype == ORC_BOOL) return ORC_ERR_UNSUPPORTED; /* bool: CDatatype but not Number */
+    const int is_signed = (dtype == ORC_I32 || dtype == ORC_I64 || dtype == ORC_I8 || dtype == ORC_I16);
     for (int i = 0; i < n; i++)
         if (!int_op_supported(nd[i].op, is_signed)) return ORC_ERR_UNSUPPORTED;
     return ORC_OK;
@@ -263,6 +306,11 @@ static inline void eval_one(int dtype, const orc_node *nd, int n, const void *x,
     case ORC_I32: *(int32_t *)out = eval_i32(nd, n, *(const int32_t *)x, y ? *(const int32_t *)y : 0); break;
     case ORC_I64: *(int64_t *)out = eval_i64(nd, n, *(const int64_t *)x, y ? *(const int64_t *)y : 0); break;
     case ORC_U32: *(uint32_t *)out = eval_u32(nd, n, *(const uint32_t *)x, y ? *(const uint32_t *)y : 0); break;
+    case ORC_BF16: *(uint16_t *)out = eval_bf16(nd, n, *(const uint16_t *)x, y ? *(const uint16_t *)y : 0); break;
+    case ORC_I8: *(int8_t *)out = eval_i8(nd, n, *(const int8_t *)x, y ? *(const int8_t *)y : 0); break;
+    case ORC_I16: *(int16_t *)out = eval_i16(nd, n, *(const int16_t *)x, y ? *(const int16_t *)y : 0); break;
+    case ORC_U16: *(uint16_t *)out = eval_u16(nd, n, *(const uint16_t *)x, y ? *(const uint16_t *)y : 0); break;
+    case ORC_U64: *(uint64_t *)out = eval_u64(nd, n, *(const uint64_t *)x, y ? *(const uint64_t *)y : 0); break;
     default: *(uint8_t *)out = eval_u8(nd, n, *(const uint8_t *)x, y ? *(const uint8_t *)y : 0); break;
     }
 }
@@ -398,6 +446,28 @@ int orc_add_unary_grad(int dtype, const orc_node *nodes, int n, const void *lhs,
             uint32_t g = eval_u32(nodes, n, ((const uint32_t *)lhs)[i], 0);
             ((uint32_t *)lhs_grad)[i] = ((uint32_t *)lhs_grad)[i] + ((const uint32_t *)out_grad)[i] * g;
         } break;
+        case ORC_BF16: {
+            uint16_t g = eval_bf16(nodes, n, ((const uint16_t *)lhs)[i], 0);
+            uint16_t m = orc_f32_to_bf16(orc_bf16_to_f32(((const uint16_t *)out_grad)[i]) * orc_bf16_to_f32(g));
+            ((uint16_t *)lhs_grad)[i] =
+                orc_f32_to_bf16(orc_bf16_to_f32(((uint16_t *)lhs_grad)[i]) + orc_bf16_to_f32(m));
+        } break;
+        case ORC_I8: {
+            uint8_t g = (uint8_t)eval_i8(nodes, n, ((const int8_t *)lhs)[i], 0);
+            ((uint8_t *)lhs_grad)[i] = (uint8_t)(((uint8_t *)lhs_grad)[i] + (uint8_t)(((const uint8_t *)out_grad)[i] * g));
+        } break;
+        case ORC_I16: {
+            uint16_t g = (uint16_t)eval_i16(nodes, n, ((const int16_t *)lhs)[i], 0);
+            ((uint16_t *)lhs_grad)[i] = (uint16_t)(((uint16_t *)lhs_grad)[i] + (uint16_t)((uint32_t)((const uint16_t *)out_grad)[i] * g));
+        } break;
+        case ORC_U16: {
+            uint16_t g = eval_u16(nodes, n, ((const uint16_t *)lhs)[i], 0);
+            ((uint16_t *)lhs_grad)[i] = (uint16_t)(((uint16_t *)lhs_grad)[i] + (uint16_t)((uint32_t)((const uint16_t *)out_grad)[i] * g));
+        } break;
+        case ORC_U64: {
+            uint64_t g = eval_u64(nodes, n, ((const uint64_t *)lhs)[i], 0);
+            ((uint64_t *)lhs_grad)[i] = ((uint64_t *)lhs_grad)[i] + ((const uint64_t *)out_grad)[i] * g;
+        } break;
         default: {
             uint8_t g = eval_u8(nodes, n, ((const uint8_t *)lhs)[i], 0);
             ((uint8_t *)lhs_grad)[i] = (uint8_t)(((uint8_t *)lhs_grad)[i] + (uint8_t)(((const uint8_t *)out_grad)[i] * g));
@@ -446,6 +516,11 @@ int orc_sum_seq(int dtype, const void *in, size_t len, void *out)
     case ORC_I64: { uint64_t s = 0; for (size_t i = 0; i < len; i++) s += (uint64_t)((const int64_t *)in)[i]; *(int64_t *)out = (int64_t)s; } break;
     case ORC_U32: { int64_t s = 0; for (size_t i = 0; i < len; i++) s += ((const uint32_t *)in)[i]; *(int64_t *)out = s; } break;
     case ORC_U8: { int64_t s = 0; for (size_t i = 0; i < len; i++) s += ((const uint8_t *)in)[i]; *(int64_t *)out = s; } break;
+    case ORC_BF16: { float s = 0.f; for (size_t i = 0; i < len; i++) s = s + orc_bf16_to_f32(((const uint16_t *)in)[i]); *(float *)out = s; } break;
+    case ORC_I8: { int64_t s = 0; for (size_t i = 0; i < len; i++) s += ((const int8_t *)in)[i]; *(int64_t *)out = s; } break;
+    case ORC_I16: { int64_t s = 0; for (size_t i = 0; i < len; i++) s += ((const int16_t *)in)[i]; *(int64_t *)out = s; } break;
+    case ORC_U16: { int64_t s = 0; for (size_t i = 0; i < len; i++) s += ((const uint16_t *)in)[i]; *(int64_t *)out = s; } break;
+    case ORC_U64: { uint64_t s = 0; for (size_t i = 0; i < len; i++) s += ((const uint64_t *)in)[i]; *(int64_t *)out = (int64_t)s; } break;
     default: return ORC_ERR_ARG;
     }
     return ORC_OK;
@@ -462,6 +537,11 @@ double orc_sum_f64(int dtype, const void *in, size_t len)
     case ORC_I64: for (size_t i = 0; i < len; i++) s += (double)((const int64_t *)in)[i]; break;
     case ORC_U32: for (size_t i = 0; i < len; i++) s += (double)((const uint32_t *)in)[i]; break;
     case ORC_U8: for (size_t i = 0; i < len; i++) s += (double)((const uint8_t *)in)[i]; break;
+    case ORC_BF16: for (size_t i = 0; i < len; i++) s += (double)orc_bf16_to_f32(((const uint16_t *)in)[i]); break;
+    case ORC_I8: for (size_t i = 0; i < len; i++) s += (double)((const int8_t *)in)[i]; break;
+    case ORC_I16: for (size_t i = 0; i < len; i++) s += (double)((const int16_t *)in)[i]; break;
+    case ORC_U16: for (size_t i = 0; i < len; i++) s += (double)((const uint16_t *)in)[i]; break;
+    case ORC_U64: for (size_t i = 0; i < len; i++) s += (double)((const uint64_t *)in)[i]; break;
     default: break;
     }
     return s;
@@ -514,20 +594,21 @@ DEFINE_BLOCK_SUM(block_sum_f64, double)
 
 static float get_f32(const void *p, size_t i) { return ((const float *)p)[i]; }
 static float get_f16(const void *p, size_t i) { return orc_f16_to_f32(((const uint16_t *)p)[i]); }
+static float get_bf16(const void *p, size_t i) { return orc_bf16_to_f32(((const uint16_t *)p)[i]); }
 static double get_f64(const void *p, size_t i) { return ((const double *)p)[i]; }
 
 int orc_sum_two_pass(int dtype, const void *in, size_t len, int blocks, size_t chunk, int threads,
                      int vec, int threads2, void *out)
 {
     if (blocks <= 0 || threads % 32 || threads2 % 32 || vec < 1 || vec > 16) return ORC_ERR_ARG;
-    if (dtype == ORC_F32 || dtype == ORC_F16) {
+    if (dtype == ORC_F32 || dtype == ORC_F16 || dtype == ORC_BF16) {
         float *partials = (float *)calloc((size_t)blocks, sizeof(float));
         const size_t sz = orc_dtype_size(dtype);
         for (int b = 0; b < blocks; b++) {
             size_t begin = (size_t)b * chunk;
             if (begin >= len) { partials[b] = 0.f; continue; }
             size_t cnt = len - begin < chunk ? len - begin : chunk;
-            partials[b] = block_sum_f32(dtype == ORC_F32 ? get_f32 : get_f16, (const char *)in + begin * sz, cnt, threads, vec);
+            partials[b] = block_sum_f32(dtype == ORC_F32 ? get_f32 : (dtype == ORC_F16 ? get_f16 : get_bf16), (const char *)in + begin * sz, cnt, threads, vec);
         }
         *(float *)out = block_sum_f32(get_f32, partials, (size_t)blocks, threads2, 1);
         free(partials);

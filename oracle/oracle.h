@@ -22,7 +22,8 @@ extern "C" {
 #endif
 
 /* same numbering as include/custos_b200.h (cb_dtype / cb_opcode / cb_node) */
-enum { ORC_F32 = 0, ORC_F64 = 1, ORC_F16 = 2, ORC_I32 = 3, ORC_I64 = 4, ORC_U32 = 5, ORC_U8 = 6 };
+enum { ORC_F32 = 0, ORC_F64 = 1, ORC_F16 = 2, ORC_I32 = 3, ORC_I64 = 4, ORC_U32 = 5, ORC_U8 = 6,
+       ORC_BF16 = 7, ORC_I8 = 8, ORC_I16 = 9, ORC_U16 = 10, ORC_U64 = 11, ORC_BOOL = 12, ORC_DTYPE_COUNT = 13 };
 enum {
     ORC_OP_X = 0, ORC_OP_Y, ORC_OP_CONST, ORC_OP_ADD, ORC_OP_MUL, ORC_OP_SUB, ORC_OP_DIV, ORC_OP_POW,
     ORC_OP_MIN, ORC_OP_MAX, ORC_OP_SIN, ORC_OP_COS, ORC_OP_TAN, ORC_OP_TANH, ORC_OP_EXP, ORC_OP_LN,
@@ -42,6 +43,8 @@ size_t orc_dtype_size(int dtype);
 /* half crate 2.x software conversions (round to nearest even) */
 uint16_t orc_f32_to_f16(float v);
 float orc_f16_to_f32(uint16_t h);
+uint16_t orc_f32_to_bf16(float v); /* half::bf16::from_f32 */
+float orc_bf16_to_f32(uint16_t h);
 
 /* Eval::eval of one expression on scalars (src/two_way_ops/eval.rs, ops.rs, ops/unary.rs, ops/cmps.rs) */
 int orc_eval(int dtype, const orc_node *nodes, int n, const void *x, const void *y, void *out);

@@ -14,9 +14,12 @@ import numpy as np
 HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "liboracle.so"
 
-F32, F64, F16, I32, I64, U32, U8 = range(7)
-NP_DTYPE = {F32: np.float32, F64: np.float64, F16: np.float16, I32: np.int32, I64: np.int64, U32: np.uint32, U8: np.uint8}
-ACC_DTYPE = {F32: np.float32, F16: np.float32, F64: np.float64, I32: np.int64, I64: np.int64, U32: np.int64, U8: np.int64}
+F32, F64, F16, I32, I64, U32, U8, BF16, I8, I16, U16, U64, BOOL = range(13)
+# bf16 buffers are uint16 bit patterns (numpy has no bfloat16)
+NP_DTYPE = {F32: np.float32, F64: np.float64, F16: np.float16, I32: np.int32, I64: np.int64, U32: np.uint32, U8: np.uint8,
+            BF16: np.uint16, I8: np.int8, I16: np.int16, U16: np.uint16, U64: np.uint64, BOOL: np.bool_}
+ACC_DTYPE = {F32: np.float32, F16: np.float32, BF16: np.float32, F64: np.float64, I32: np.int64, I64: np.int64, U32: np.int64,
+             U8: np.int64, I8: np.int64, I16: np.int64, U16: np.int64, U64: np.int64}
 
 
 class orc_node(C.Structure):
@@ -45,6 +48,8 @@ def lib() -> C.CDLL:
         progs = C.POINTER(C.POINTER(orc_node))
         L.orc_f32_to_f16.argtypes, L.orc_f32_to_f16.restype = [C.c_float], C.c_uint16
         L.orc_f16_to_f32.argtypes, L.orc_f16_to_f32.restype = [C.c_uint16], C.c_float
+        L.orc_f32_to_bf16.argtypes, L.orc_f32_to_bf16.restype = [C.c_float], C.c_uint16
+        L.orc_bf16_to_f32.argtypes, L.orc_bf16_to_f32.restype = [C.c_uint16], C.c_float
         L.orc_eval.argtypes = [i32, nodes, i32, vp, vp, vp]
         L.orc_apply_fn.argtypes = [i32, nodes, i32, vp, vp, sz]
         L.orc_apply_chain.argtypes = [i32, progs, C.POINTER(C.c_int), i32, vp, vp, sz]
@@ -182,6 +187,14 @@ def f32_to_f16_bits(v: float) -> int:
 
 def f16_bits_to_f32(h: int) -> float:
     return float(lib().orc_f16_to_f32(C.c_uint16(h)))
+
+
+def f32_to_bf16_bits(v: float) -> int:
+    return int(lib().orc_f32_to_bf16(C.c_float(v)))
+
+
+def bf16_bits_to_f32(h: int) -> float:
+    return float(lib().orc_bf16_to_f32(C.c_uint16(h)))
 
 
 class Graph:

@@ -75,6 +75,16 @@ def single_gpu(n):
     c16 = dev.compile(CHEAP8, N.F16)
     out["cheap8_fwd_f16"] = row(timeit(dev, lambda: dev.apply(c16, b, c, n)), n, 4)
     dev.free(ph)
+    # bf16: same inputs rounded to bfloat16
+    from custos_b200.expr import bf16_from_f32
+    pb = dev.upload(bf16_from_f32(np.random.default_rng(4).uniform(-4, 4, 1 << 24).astype(np.float32)))
+    for off in range(0, n, 1 << 24):
+        dev.copy(N.BF16, b, off, pb, 0, min(1 << 24, n - off))
+    eb = dev.compile(CHAIN8, N.BF16)
+    out["chain8_fwd_bf16"] = row(timeit(dev, lambda: dev.apply(eb, b, c, n)), n, 4)
+    cb = dev.compile(CHEAP8, N.BF16)
+    out["cheap8_fwd_bf16"] = row(timeit(dev, lambda: dev.apply(cb, b, c, n)), n, 4)
+    dev.free(pb)
     for off in range(0, n, 1 << 24):  # restore b
         dev.copy(N.F32, b, off, ps, 0, min(1 << 24, n - off))
     cheap = dev.compile(CHEAP8, N.F32)

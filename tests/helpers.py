@@ -3,8 +3,12 @@ import numpy as np
 
 from custos_b200 import _native as N
 
+from custos_b200.expr import bf16_from_f32, bf16_to_f32  # noqa: E402
+
+# bf16 buffers are uint16 bit patterns on the host (numpy has no bfloat16)
 NP = {N.F32: np.float32, N.F64: np.float64, N.F16: np.float16, N.I32: np.int32, N.I64: np.int64,
-      N.U32: np.uint32, N.U8: np.uint8}
+      N.U32: np.uint32, N.U8: np.uint8, N.BF16: np.uint16, N.I8: np.int8, N.I16: np.int16, N.U16: np.uint16,
+      N.U64: np.uint64, N.BOOL: np.bool_}
 UINT_OF = {N.F32: np.uint32, N.F64: np.uint64, N.F16: np.uint16}
 INT_OF = {N.F32: np.int64, N.F64: np.int64, N.F16: np.int64}
 
@@ -51,6 +55,34 @@ def assert_bit_exact(got: np.ndarray, want: np.ndarray, what: str = ""):
         raise AssertionError(f"{what}: {bad.size} of {got.size} elements differ; first at {i}: got {got[i]!r} want {want[i]!r}")
 
 
+def bf16_is_nan(b: np.ndarray) -> np.ndarray:
+    return (b & 0x7fff) > 0x7f80
+
+
+def assert_bf16_bit_exact(got: np.ndarray, want: np.ndarray, what: str = ""):
+    """bf16 bit patterns; NaN payloads are not compared (cvt.rn.bf16.f32 canonicalises, `half` keeps bits)."""
+    same = (got == want) | (bf16_is_nan(got) & bf16_is_nan(want))
+    if not np.all(same):
+        bad = np.flatnonzero(~same)
+        i = bad[0]
+        raise AssertionError(f"{what}: {bad.size} of {got.size} bf16 elements differ; first at {i}: "
+                             f"got {int(got[i]):#06x} want {int(want[i]):#06x}")
+
+
+def bf16_ulp_distance(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    ua, ub = a.astype(np.int64), b.astype(np.int64)
+    oa = np.where(ua & 0x8000, 0x8000 - ua, ua)
+    ob = np.where(ub & 0x8000, 0x8000 - ub, ub)
+    d = np.abs(oa - ob).astype(np.float64)
+    na, nb = bf16_is_nan(a), bf16_is_nan(b)
+    d = np.where(na & nb, 0.0, d)
+    return np.where(na ^ nb, 1e30, d)
+
+
+def assert_same(dt: int, got: np.ndarray, want: np.ndarray, what: str = ""):
+    (assert_bf16_bit_exact if dt == N.BF16 else assert_bit_exact)(got, want, what)
+
+
 def assert_ulp(got: np.ndarray, want: np.ndarray, max_ulp: float, what: str = ""):
     d = ulp_distance(got, want)
     worst = int(np.argmax(d))
@@ -72,6 +104,10 @@ def edge_values(np_dtype) -> np.ndarray:
 def random_inputs(dtype_code: int, n: int, seed: int, lo=-4.0, hi=4.0) -> np.ndarray:
     rng = np.random.default_rng(seed)
     t = NP[dtype_code]
+    if dtype_code == N.BF16:
+        return bf16_from_f32(rng.uniform(lo, hi, n).astype(np.float32))
+    if dtype_code == N.BOOL:
+        return rng.integers(0, 2, n).astype(np.bool_)
     if np.dtype(t).kind == "f":
         return rng.uniform(lo, hi, n).astype(t)
     info = np.iinfo(t)

@@ -47,7 +47,7 @@ def test_no_link_time_dependency_on_the_driver_or_the_oracle():
 def test_abi_version_and_dtype_sizes():
     lib = N.load()
     assert lib.cb_abi_version() == 1
-    assert [lib.cb_dtype_size(i) for i in range(7)] == [4, 8, 2, 4, 8, 4, 1]
+    assert [lib.cb_dtype_size(i) for i in range(13)] == [4, 8, 2, 4, 8, 4, 1, 2, 1, 2, 2, 8, 1]  # every CDatatype
     assert lib.cb_dtype_size(99) == 0
 
 

@@ -84,9 +84,9 @@ def test_invalid_programs_are_rejected():
     assert N.load().cb_expr_to_cl_source(N.F32, bad, 1, b"x", b"y", buf, 64) == N.CB_ERR_EXPR
 
 
-@pytest.mark.parametrize("dt", range(7))
+@pytest.mark.parametrize("dt", range(12))
 def test_every_kernel_kind_compiles_for_sm_100a(dt):
-    f = (lambda x: x.mul(2.0).add(1.0).sin().exp().ln().tanh().abs().neg()) if dt in (N.F32, N.F64, N.F16) else (lambda x: x.mul(2).add(1))
+    f = (lambda x: x.mul(2.0).add(1.0).sin().exp().ln().tanh().abs().neg()) if dt in E.FLOAT_DTYPES else (lambda x: x.mul(2).add(1))
     assert E.compile_check([f], dt, N.KERNEL_APPLY) > 1000
     assert E.compile_check([f], dt, N.KERNEL_UNARY_GRAD) > 1000
     assert E.compile_check([lambda x, y: x.mul(y).sub(x)], dt, N.KERNEL_BINARY, n_args=2) > 1000
@@ -100,7 +100,29 @@ def test_benchmark_chains_compile():
         assert E.compile_check([g], N.F32, N.KERNEL_UNARY_GRAD) > 1000
 
 
+def test_bool_is_storage_only():
+    # bool is a CDatatype (cdatatype.rs:7-9) but not a Number: no expression can be built over it
+    with pytest.raises(CustosError) as ei:
+        E.compile_check([lambda x: x.add(1)], N.BOOL)
+    assert ei.value.code == N.CB_ERR_UNSUPPORTED
+
+
+def test_new_dtype_literals_and_sources():
+    # half's Debug for bf16 prints the f32 value of the ROUNDED literal
+    assert E.to_cl_source(lambda x: x.add(1.3).mul(2.0), N.BF16) == "((x + 1.296875) * 2.0)"
+    assert E.to_cl_source(lambda x: x.add(-3), N.I8) == "(x + -3)"
+    assert E.to_cl_source(lambda x: x.mul(65535), N.U16) == "(x * 65535)"
+    assert E.to_cl_source(lambda x: x.add(18446744073709551615), N.U64) == "(x + 18446744073709551615)"
+    src = E.cuda_source([lambda x: x.mul(1.5)], N.BF16)
+    assert "cbw_mul_c(t0, (T)0x3fc0u)" in src and "((T)0x3fc0u)" in src
+    with pytest.raises(CustosError):  # unsigned types have no Neg in Rust
+        E.compile_check([lambda x: x.neg()], N.U16)
+    assert E.compile_check([lambda x: x.neg()], N.I16) > 1000
+
+
 def test_literals_round_to_the_dtype():
+    arr, n = E.flatten(lambda x: x.mul(0.1), N.BF16)
+    assert arr[1].fimm == 0.10009765625
     arr, n = E.flatten(lambda x: x.mul(0.1), N.F16)
     assert arr[1].fimm == float(np.float16(0.1))
     arr, n = E.flatten(lambda x: x.mul(0.1), N.F32)

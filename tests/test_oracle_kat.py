@@ -212,6 +212,68 @@ def test_f16_tan_is_cos_like_the_reference():
     assert np.array_equal(orc.apply_fn(lambda v: v.tan(), F16, x), orc.apply_fn(lambda v: v.cos(), F16, x))
 
 
+def test_f16_max_is_halfs_inherent_max():
+    # src/number.rs:537-539: Number::max for f16 forwards to half's f16::max, which keeps `self` unless
+    # `other > self`; the trait default (f32, f64, bf16; number.rs:202-204) returns `rhs` unless `self > rhs`.
+    # The two only differ for equal values with different bits (+0 / -0) and for NaN operands.
+    pz, nz = np.float16(0.0), np.float16(-0.0)
+    assert orc.eval_scalar(lambda x, y: x.max(y), F16, pz, nz).view(np.uint16) == 0x0000
+    assert orc.eval_scalar(lambda x, y: x.max(y), F16, nz, pz).view(np.uint16) == 0x8000
+    assert orc.eval_scalar(lambda x, y: x.max(y), F32, 0.0, -0.0).view(np.uint32) == 0x80000000
+    assert orc.eval_scalar(lambda x, y: x.max(y), orc.BF16, 0x0000, 0x8000) == 0x8000
+    assert orc.eval_scalar(lambda x, y: x.min(y), F16, pz, nz).view(np.uint16) == 0x8000  # default min: rhs
+
+
+# ------------------------------------------------------------------ bf16 (parity unpinned in the reference)
+def test_bf16_conversions_are_rne_with_halfs_nan_rule():
+    cases = [(1.0, 0x3F80), (-2.0, 0xC000), (0.0, 0x0000), (-0.0, 0x8000), (float("inf"), 0x7F80), (3.4e38, 0x7F80),
+             (3.3895314e38, 0x7F7F), (1e-40, 0x0001)]
+    for v, bits in cases:
+        assert orc.f32_to_bf16_bits(v) == bits, v
+    f = lambda u: float(np.array([u], np.uint32).view(np.float32)[0])
+    assert orc.f32_to_bf16_bits(f(0x3F808000)) == 0x3F80   # tie -> even (down)
+    assert orc.f32_to_bf16_bits(f(0x3F818000)) == 0x3F82   # tie -> even (up)
+    assert orc.f32_to_bf16_bits(f(0x3F808001)) == 0x3F81   # above the tie
+    assert orc.f32_to_bf16_bits(f(0x7F7FFFFF)) == 0x7F80   # f32::MAX rounds to inf
+    assert orc.f32_to_bf16_bits(float("nan")) & 0x7FC0 == 0x7FC0
+    assert orc.bf16_bits_to_f32(0x3FC0) == 1.5
+    # the package's host helper (used to prepare bf16 inputs) agrees with the oracle on random values
+    from custos_b200.expr import bf16_from_f32, bf16_to_f32
+    rng = np.random.default_rng(1)
+    vals = np.concatenate([rng.standard_normal(5000).astype(np.float32) * 1e3, rng.uniform(-1e-38, 1e-38, 2000).astype(np.float32)])
+    want = np.array([orc.f32_to_bf16_bits(float(v)) for v in vals], np.uint16)
+    assert np.array_equal(bf16_from_f32(vals), want)
+    assert np.array_equal(bf16_to_f32(want), np.array([orc.bf16_bits_to_f32(int(b)) for b in want], np.float32))
+
+
+def test_bf16_rounds_after_every_op_and_tan_is_cos():
+    # src/number.rs:611-676: each op goes bf16 -> f32 -> bf16; `tan` calls cos (:643-645)
+    from custos_b200.expr import bf16_from_f32, bf16_to_f32
+    x = bf16_from_f32(np.array([0.1, 1.5, 3.25, -2.0], np.float32))
+    out = orc.apply_fn(lambda v: v.mul(3.0).add(0.1).exp(), orc.BF16, x)
+    r = lambda a: bf16_to_f32(bf16_from_f32(a))
+    step = r(r(bf16_to_f32(x) * np.float32(3.0)) + r(np.float32([0.1]))[0])
+    assert np.array_equal(out, bf16_from_f32(np.exp(step)))
+    assert np.array_equal(orc.apply_fn(lambda v: v.tan(), orc.BF16, x), orc.apply_fn(lambda v: v.cos(), orc.BF16, x))
+
+
+def test_narrow_and_wide_integers_wrap():
+    # release-mode Rust arithmetic wraps; i8 / i16 / u16 / u64 are CDatatypes (cdatatype.rs:28-51)
+    assert orc.eval_scalar(lambda x: x.add(100), orc.I8, 100) == np.int8(-56)
+    assert orc.eval_scalar(lambda x: x.mul(3), orc.I16, 20000) == np.int16(60000 - 65536)
+    assert orc.eval_scalar(lambda x: x.sub(1), orc.U16, 0) == 65535
+    assert orc.eval_scalar(lambda x: x.add(2), orc.U64, 2 ** 64 - 1) == 1
+    assert orc.eval_scalar(lambda x: x.neg(), orc.I8, -128) == np.int8(-128)
+    assert orc.eval_scalar(lambda x: x.div(-1), orc.I8, -128) == np.int8(-128)   # Rust panics; defined as wrap
+    assert orc.eval_scalar(lambda x: x.div(0), orc.I16, 5) == 0                  # Rust panics; defined as 0
+    assert orc.sum_seq(orc.I8, np.full(1000, -128, np.int8)) == -128000
+    assert orc.sum_seq(orc.U16, np.full(1000, 65535, np.uint16)) == 65_535_000
+    with pytest.raises(orc.OracleError):
+        orc.apply_fn(lambda x: x.neg(), orc.U16, [1])
+    with pytest.raises(orc.OracleError):
+        orc.apply_fn(lambda x: x.add(1), orc.BOOL, [True])
+
+
 # ------------------------------------------------------------------ sums (order defined by this project)
 def test_two_pass_sum_matches_f64_ground_truth():
     rng = np.random.default_rng(5)
