@@ -28,6 +28,7 @@ struct cb_expr {
     int resident_vec = 0;     // blocks of the vector / scalar kernel one SM holds (occupancy query):
     int resident_scalar = 0;  // the persistent grid is exactly one wave of them
     size_t cubin_bytes = 0;
+    std::string ir;  // canonical bytes of (dtype, kind, programs): identity of the cached kernel
 };
 
 struct cb_graph {
@@ -85,7 +86,9 @@ struct cb_device {
     uint64_t launches = 0;
     bool capturing = false;
 
-    std::unordered_map<uint64_t, std::unique_ptr<cb_expr>> exprs;  // kernel cache keyed by IR hash
+    // kernel cache keyed by the IR hash; a bucket holds every expression with that hash and a hit is
+    // confirmed against the stored IR bytes, so a 64-bit collision costs a compile, never a wrong kernel
+    std::unordered_map<uint64_t, std::vector<std::unique_ptr<cb_expr>>> exprs;
 
     struct Slot {
         uint64_t ptr;

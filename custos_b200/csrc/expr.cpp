@@ -401,33 +401,42 @@ std::string expr_cuda_function(int32_t dtype, const cb_node *const *progs, const
     return s;
 }
 
-uint64_t chain_hash(int32_t dtype, int32_t kind, const cb_node *const *progs, const int32_t *n_nodes,
-                    int32_t n_progs)
+std::string chain_bytes(int32_t dtype, int32_t kind, const cb_node *const *progs, const int32_t *n_nodes,
+                        int32_t n_progs)
 {
-    uint64_t h = 1469598103934665603ull;
-    auto mix = [&h](uint64_t v) {
-        for (int i = 0; i < 8; i++) {
-            h ^= (v >> (8 * i)) & 0xffu;
-            h *= 1099511628211ull;
-        }
+    std::string out;
+    auto put = [&out](uint64_t v) {
+        for (int i = 0; i < 8; i++) out.push_back((char)((v >> (8 * i)) & 0xffu));
     };
-    mix((uint64_t)dtype);
-    mix((uint64_t)kind);
-    mix((uint64_t)n_progs);
+    put((uint64_t)dtype);
+    put((uint64_t)kind);
+    put((uint64_t)n_progs);
     for (int32_t k = 0; k < n_progs; k++) {
-        mix((uint64_t)n_nodes[k]);
+        put((uint64_t)n_nodes[k]);
         for (int32_t i = 0; i < n_nodes[k]; i++) {
             const cb_node &c = progs[k][i];
-            mix((uint64_t)(uint32_t)c.op);
-            mix((uint64_t)(uint32_t)c.a);
-            mix((uint64_t)(uint32_t)c.b);
+            put((uint64_t)(uint32_t)c.op);
+            put((uint64_t)(uint32_t)c.a);
+            put((uint64_t)(uint32_t)c.b);
             if (c.op == CB_OP_CONST) {
                 uint64_t bits;
                 if (is_float_dtype(dtype)) std::memcpy(&bits, &c.fimm, 8);
                 else bits = (uint64_t)c.iimm;
-                mix(bits);
+                put(bits);
             }
         }
+    }
+    return out;
+}
+
+// FNV-1a over chain_bytes
+uint64_t chain_hash(int32_t dtype, int32_t kind, const cb_node *const *progs, const int32_t *n_nodes,
+                    int32_t n_progs)
+{
+    uint64_t h = 1469598103934665603ull;
+    for (unsigned char ch : chain_bytes(dtype, kind, progs, n_nodes, n_progs)) {
+        h ^= ch;
+        h *= 1099511628211ull;
     }
     return h;
 }

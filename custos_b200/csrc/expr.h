@@ -32,6 +32,9 @@ std::string expr_cuda_function(int32_t dtype, const cb_node *const *progs, const
                                int32_t n_progs);
 
 // 64-bit key of (dtype, kind, programs) for the kernel cache
+// canonical byte string of (dtype, kind, programs): what chain_hash hashes, kept to confirm cache hits
+std::string chain_bytes(int32_t dtype, int32_t kind, const cb_node *const *progs, const int32_t *n_nodes,
+                        int32_t n_progs);
 uint64_t chain_hash(int32_t dtype, int32_t kind, const cb_node *const *progs, const int32_t *n_nodes,
                     int32_t n_progs);
 
