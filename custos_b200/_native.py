@@ -30,7 +30,8 @@ class cb_node(C.Structure):
 CB_OK = 0
 CB_ERR_INVALID_ARG, CB_ERR_ZERO_LENGTH, CB_ERR_NO_DEVICE, CB_ERR_UNSUPPORTED, CB_ERR_EXPR = 1, 2, 3, 4, 5
 CB_ERR_INVALID_LAZY_BUF, CB_ERR_MISSING_CACHE_TRACES, CB_ERR_GRAPH_OPTIMIZATION = 6, 7, 8
-CB_ERR_SHAPE, CB_ERR_STATE = 9, 10
+CB_ERR_SHAPE, CB_ERR_STATE, CB_ERR_TYPE_MISMATCH, CB_ERR_PARSE = 9, 10, 11, 12
+SER_JSON, SER_BINCODE = 0, 1
 F32, F64, F16, I32, I64, U32, U8, BF16, I8, I16, U16, U64, BOOL = range(13)
 KERNEL_APPLY, KERNEL_UNARY_GRAD, KERNEL_BINARY = 0, 1, 2
 BIN_ADD, BIN_MUL, BIN_SUB, BIN_DIV = 0, 1, 2, 3
@@ -143,6 +144,14 @@ SIGNATURES = {
     "cbm_grad": [_vp, _u64, _P(_u64)],
     "cbm_zero_grad": [_vp],
     "cbm_set_grad_enabled": [_vp, _i32],
+    # untyped views and serde
+    "cbm_buffer_dtype": [_vp, _u64, _P(_i32)],
+    "cbm_buffer_matches_type": [_vp, _u64, _i32],
+    "cbm_buffer_read_typed": [_vp, _u64, _i32, _vp, _sz],
+    "cb_serde_encode": [_i32, _i32, _vp, _sz, _vp, _sz, _P(_sz)],
+    "cb_serde_decode": [_i32, _i32, _vp, _sz, _vp, _sz, _P(_sz)],
+    "cbm_buffer_serialize": [_vp, _u64, _i32, _vp, _sz, _P(_sz)],
+    "cbm_buffer_deserialize": [_vp, _i32, _i32, _vp, _sz, _P(_u64)],
     # device-free graph analysis
     "cb_optgraph_create": [_P(_vp)],
     "cb_optgraph_destroy": [_vp],
@@ -153,7 +162,8 @@ SIGNATURES = {
     "cb_optgraph_trace_cache_path_raw": [_vp, _i64, _P(_i64), _sz, _P(_sz)],
     "cb_optgraph_cache_traces": [_vp, _P(_i64), _sz, _P(_sz)],
 }
-_OTHER_RESTYPE = {"cb_last_error": ([], C.c_char_p), "cb_abi_version": ([], _i32), "cb_dtype_size": ([_i32], _sz)}
+_OTHER_RESTYPE = {"cb_last_error": ([], C.c_char_p), "cb_abi_version": ([], _i32), "cb_dtype_size": ([_i32], _sz),
+                   "cbm_untyped_supports": ([_i32], _i32)}
 
 _lib = None
 

@@ -497,6 +497,14 @@ extern "C" int32_t cbm_buffer_len(cbm_device *d, cbm_buf b, size_t *len)
     return CB_OK;
 }
 
+extern "C" int32_t cbm_buffer_dtype(cbm_device *d, cbm_buf b, int32_t *dtype)
+{
+    CB_CHECK_ARG(d && dtype, "null argument");
+    GET_HANDLE(h, d, b);
+    *dtype = h->dtype;
+    return CB_OK;
+}
+
 static int32_t storage_of(cbm_device *d, const Handle *h, Entry *out)
 {
     if (!h->lazy && h->ptr && !d->resolve(h->id)) {  // gradient views and the like

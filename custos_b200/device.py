@@ -54,6 +54,8 @@ class Buffer:
         return self
 
     def read(self) -> np.ndarray:
+        if self.dtype is None:
+            raise TypeError("an untyped buffer has no element type: use read_typed(dtype) or to_typed(dtype)")
         out = np.empty(len(self), NP_DTYPE[self.dtype])
         N.call("cbm_buffer_read", self.device.h, self.handle, out.ctypes.data_as(C.c_void_p), out.size)
         return out
@@ -103,6 +105,52 @@ class Buffer:
     def drop(self) -> None:
         """End of the Rust scope of the buffer."""
         N.call("cbm_buffer_drop", self.device.h, self.handle)
+
+    # ------------------------------------------------------------ untyped views (src/devices/untyped/mod.rs:17-84)
+    def storage_dtype(self) -> int:
+        """The run-time tag of the storage (`UntypedData` / `CudaStorage` variant)."""
+        v = C.c_int32()
+        N.call("cbm_buffer_dtype", self.device.h, self.handle, C.byref(v))
+        return v.value
+
+    def to_untyped(self) -> "Buffer":
+        """Buffer::to_untyped / as_untyped: the same buffer without static type information."""
+        return Buffer(self.device, self.handle, None)
+
+    as_untyped = to_untyped
+
+    def to_typed(self, dtype) -> "Buffer | None":
+        """Buffer::to_typed / as_typed: `None` when the storage holds another type."""
+        dt = dtype_code(dtype)
+        rc = N.load().cbm_buffer_matches_type(self.device.h, self.handle, dt)
+        if rc == N.CB_ERR_TYPE_MISMATCH:
+            return None
+        N.check(rc)
+        return Buffer(self.device, self.handle, dt)
+
+    as_typed = to_typed
+
+    def read_typed(self, dtype) -> "np.ndarray | None":
+        """Buffer::read_typed::<OT>()"""
+        typed = self.to_typed(dtype)
+        return None if typed is None else typed.read()
+
+    # ------------------------------------------------------------ serde (src/devices/cuda/cuda_ptr.rs:122-157)
+    def serialize(self, fmt: int = N.SER_JSON) -> bytes:
+        """The buffer as a serialised sequence of its elements: serde_json text or bincode bytes."""
+        need = C.c_size_t()
+        N.call("cbm_buffer_serialize", self.device.h, self.handle, fmt, None, 0, C.byref(need))
+        out = C.create_string_buffer(max(need.value, 1))
+        N.call("cbm_buffer_serialize", self.device.h, self.handle, fmt, out, need.value, C.byref(need))
+        return out.raw[:need.value]
+
+    def to_tokens(self) -> list:
+        """The serde data-model view `serde_test` asserts on: Seq { len }, one token per element, SeqEnd."""
+        dt = self.storage_dtype()
+        name = {N.F32: "F32", N.F64: "F64", N.I8: "I8", N.I16: "I16", N.I32: "I32", N.I64: "I64", N.U8: "U8",
+                N.U16: "U16", N.U32: "U32", N.U64: "U64", N.BOOL: "Bool"}[dt]
+        vals = Buffer(self.device, self.handle, dt).read().tolist()
+        return [("Seq", len(vals))] + [(name, v) for v in vals] + [("SeqEnd",)]
 
 
 class CUDA:
@@ -226,6 +274,13 @@ class CUDA:
         N.call("cbm_mean", self.h, buf.handle, out.ctypes.data_as(C.c_void_p))
         return out[0]
 
+    def deserialize(self, data: bytes, dtype, fmt: int = N.SER_JSON) -> Buffer:
+        """Deserialize for CUDAPtr<T>: collect the sequence, allocate, write (cuda_ptr.rs:141-156)."""
+        dt = dtype_code(dtype)
+        out = C.c_uint64()
+        N.call("cbm_buffer_deserialize", self.h, dt, fmt, C.c_char_p(data), len(data), C.byref(out))
+        return Buffer(self, out.value, dt)
+
     # ------------------------------------------------------------ Lazy
     def run(self) -> None:
         N.call("cbm_run", self.h)
@@ -307,3 +362,37 @@ class CUDA:
 
     def sync(self) -> None:
         self.raw.sync()
+
+
+class Untyped(CUDA):
+    """`Untyped` (src/devices/untyped/untyped_device.rs:16-72): a `CUDA<Base>` whose buffers are told apart by
+    a run-time storage tag.  Only the `AsType` types are accepted (matches_type.rs:28-71); ops dispatch on
+    the tag like `untyped_binary_op!` (ops.rs:80-159) and fail where the reference hits `unimplemented!()`."""
+
+    def __init__(self, ordinal: int = 0):
+        super().__init__("Base", ordinal=ordinal)
+
+    def buffer(self, data, dtype=None) -> Buffer:
+        if dtype is None:
+            dtype = data.dtype if isinstance(data, np.ndarray) else (
+                np.float32 if np.asarray(data).dtype.kind == "f" else np.int64)
+        dt = dtype_code(dtype)
+        if not N.load().cbm_untyped_supports(dt):
+            raise TypeError(f"dtype {dt} has no AsType impl: an Untyped device cannot hold it")
+        return super().buffer(data, dtype=dt)
+
+    @staticmethod
+    def _tag(buf: Buffer) -> int:
+        return buf.storage_dtype() if buf.dtype is None else buf.dtype
+
+    def apply_fn(self, buf: Buffer, f) -> Buffer:
+        typed = Buffer(self, buf.handle, self._tag(buf))
+        out = super().apply_fn(typed, f)
+        return out.to_untyped() if buf.dtype is None else out
+
+    def _binary(self, op: int, lhs: Buffer, rhs: Buffer) -> Buffer:
+        tl, tr = self._tag(lhs), self._tag(rhs)
+        if tl != tr:
+            raise NotImplementedError(f"untyped_binary_op: storages of type {tl} and {tr}")  # `_ => unimplemented!()`
+        out = super()._binary(op, Buffer(self, lhs.handle, tl), Buffer(self, rhs.handle, tr))
+        return out.to_untyped() if lhs.dtype is None else out

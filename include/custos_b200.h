@@ -51,6 +51,8 @@ typedef enum cb_status {
     CB_ERR_GRAPH_OPTIMIZATION = 8,   /* DeviceError::GraphOptimization */
     CB_ERR_SHAPE = 9,
     CB_ERR_STATE = 10,
+    CB_ERR_TYPE_MISMATCH = 11,  /* Untyped: `matches_storage_type` failed (src/devices/untyped/storages.rs) */
+    CB_ERR_PARSE = 12,          /* malformed serialised buffer */
     CB_ERR_CUDA = 1000,
     CB_ERR_NCCL = 2000,
     CB_ERR_NVRTC = 3000
@@ -389,6 +391,41 @@ int32_t cbm_backward_with(cbm_device *d, cbm_buf out, const void *seed, size_t l
 int32_t cbm_grad(cbm_device *d, cbm_buf b, cbm_buf *grad);     /* Buffer::grad: allocates (zeroed) on first use */
 int32_t cbm_zero_grad(cbm_device *d);
 int32_t cbm_set_grad_enabled(cbm_device *d, int32_t enabled);  /* Autograd::{enable,disable}_grad */
+
+/* -------------------------------------------- Untyped buffers and serde (f4) */
+/* src/devices/untyped/: a buffer whose element type is a run-time tag (`UntypedData` = CpuStorage /
+ * CudaStorage enums, storages.rs) instead of a type parameter.  Every cbm_buf already carries its
+ * cb_dtype, so "untyped" here is a view: the tag can be queried, and typed access checks it the way
+ * `to_typed` / `as_typed` / `read_typed` do (mod.rs:17-84: `None` on a mismatch). */
+int32_t cbm_buffer_dtype(cbm_device *d, cbm_buf b, int32_t *dtype);           /* the storage tag */
+/* AsType (matches_type.rs:28-71): the types an Untyped device accepts: u8, u32, i64, bf16, f16, f32, f64 */
+int32_t cbm_untyped_supports(int32_t dtype);                                   /* 1 / 0 */
+/* MatchesType::matches_storage_type: CB_OK or CB_ERR_TYPE_MISMATCH */
+int32_t cbm_buffer_matches_type(cbm_device *d, cbm_buf b, int32_t dtype);
+/* Buffer::read_typed::<OT>() (mod.rs:77-83) */
+int32_t cbm_buffer_read_typed(cbm_device *d, cbm_buf b, int32_t dtype, void *host_out, size_t len);
+
+/* serde of device buffers (src/devices/cuda/cuda_ptr.rs:122-157): a CUDAPtr<T> serialises as the
+ * SEQUENCE of its elements (read back to the host first) and deserialises by allocating and writing.
+ * serde is format-agnostic; two concrete encodings of that sequence are provided:
+ *   CB_SER_JSON     what serde_json writes: "[1,2,3]", floats in ryu's shortest round-trip form
+ *                   ("1.0", "0.1", "1e16", "1.5e-7"), non-finite floats as null (and, like serde_json,
+ *                   a null does not deserialise into a float: CB_ERR_PARSE);
+ *   CB_SER_BINCODE  what bincode 1.x (fixint, little endian) writes: u64 length, then the elements.
+ * Only types that implement serde::Serialize in the reference build: the integers, f32, f64, bool
+ * (half is built without its serde feature, Cargo.toml:36 -> f16 / bf16: CB_ERR_UNSUPPORTED).
+ * Serialise: `*needed` receives the byte count; data is written only when cap >= *needed (call with
+ * out = NULL to size the buffer).  JSON output is not NUL-terminated. */
+typedef enum cb_ser_format { CB_SER_JSON = 0, CB_SER_BINCODE = 1 } cb_ser_format;
+/* the codec alone, host memory to host memory (no device): `elems` are n elements of dtype */
+int32_t cb_serde_encode(int32_t dtype, int32_t format, const void *elems, size_t n, void *out, size_t cap,
+                        size_t *needed);
+/* `*n` receives the element count; elements are written only when cap_elems >= *n */
+int32_t cb_serde_decode(int32_t dtype, int32_t format, const void *in, size_t len, void *elems_out,
+                        size_t cap_elems, size_t *n);
+int32_t cbm_buffer_serialize(cbm_device *d, cbm_buf b, int32_t format, void *out, size_t cap, size_t *needed);
+int32_t cbm_buffer_deserialize(cbm_device *d, int32_t dtype, int32_t format, const void *in, size_t len,
+                               cbm_buf *out);
 
 /* ------------------------------------------- OptGraph without a device (a10) */
 /* src/modules/graph/opt_graph.rs:6-41 and opt_graph/optimize.rs:19-132 */
