@@ -317,5 +317,6 @@ extern "C" int32_t cbm_buffer_deserialize(cbm_device *d, int32_t dtype, int32_t 
     CB_TRY(decode_to(dtype, format, in, len, &host, &n));
     // CUDAPtr::new(len) + cu_write (cuda_ptr.rs:151-153); a zero-length sequence fails like every
     // zero-length allocation
+    if (!n) return fail(CB_ERR_ZERO_LENGTH, "deserialised an empty sequence: a zero length buffer cannot be allocated");
     return cbm_buffer_from_host(d, dtype, host.data(), n, out);
 }
