@@ -119,7 +119,9 @@ SIGNATURES = {
     "cbm_add_unary_grad": [_vp, _u64, _u64, _u64, _nodes, _i32],
     "cbm_unary_ew": [_vp, _u64, _nodes, _i32, _nodes, _i32, _P(_u64)],
     "cbm_binary": [_vp, _i32, _u64, _u64, _P(_u64)],
+    "cbm_binary_into": [_vp, _i32, _u64, _u64, _u64],
     "cbm_clear": [_vp, _u64],
+    "cbm_clear_op": [_vp, _u64],
     "cbm_copy_slice": [_vp, _u64, _sz, _u64, _sz, _sz],
     "cbm_clone_buf": [_vp, _u64, _P(_u64)],
     "cbm_sum": [_vp, _u64, _vp],

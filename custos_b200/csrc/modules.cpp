@@ -63,7 +63,7 @@ struct Handle {
     bool owned = false;  // freed on drop (AllocFlag::None); cached and gradient buffers are not
 };
 
-enum class OpKind { NoOp, Apply, UnaryGrad, Binary, Apply2 };
+enum class OpKind { NoOp, Apply, UnaryGrad, Binary, Apply2, Clear };
 
 // Operation (src/modules/lazy/lazy_graph.rs:8-12): argument ids + what to launch + the op hint
 struct Op {
@@ -267,6 +267,8 @@ int32_t call_op(cbm_device *d, const Op &op)
         return cb_binary(d->raw, op.dtype, op.binop, arg[0]->ptr, arg[1]->ptr, arg[2]->ptr, arg[2]->len);
     case OpKind::Apply2:  // args: (lhs, rhs, out): a fused two-input expression
         return cb_apply2(d->raw, op.expr, arg[0]->ptr, arg[1]->ptr, arg[2]->ptr, arg[2]->len);
+    case OpKind::Clear:  // args: (buf)
+        return cb_clear(d->raw, op.dtype, arg[0]->ptr, arg[0]->len);
     default: return CB_OK;
     }
 }
@@ -696,6 +698,45 @@ extern "C" int32_t cbm_binary(cbm_device *d, int32_t op, cbm_buf lhs, cbm_buf rh
     if (rc != CB_OK) return rc;
     *out = ob;
     return CB_OK;
+}
+
+// A binary op whose output buffer is chosen by the caller — what the reference's tests do with their own
+// kernels: `device.launch_kernel1d(len, &add_src, "add", &[&lhs, &rhs, &mut out, &len])`
+// (src/devices/cuda/lazy.rs:96-141) or `add_op((&a, &b, &mut out), ..)` (src/modules/lazy.rs:741-751).
+// No retrieve, hence no graph node and no cache trace: the fusing passes treat it as an opaque reader /
+// writer of its three buffers.
+extern "C" int32_t cbm_binary_into(cbm_device *d, int32_t op, cbm_buf lhs, cbm_buf rhs, cbm_buf out)
+{
+    CB_CHECK_ARG(d, "null device");
+    CB_CHECK_ARG(op >= CB_BIN_ADD && op <= CB_BIN_DIV, "bad binary op");
+    GET_HANDLE(hl, d, lhs);
+    GET_HANDLE(hr, d, rhs);
+    GET_HANDLE(ho, d, out);
+    if (hl->dtype != hr->dtype || hl->dtype != ho->dtype) return fail(CB_ERR_INVALID_ARG, "dtype mismatch");
+    if (hl->len != hr->len || hl->len != ho->len)
+        return fail(CB_ERR_SHAPE, "length mismatch: %zu, %zu -> %zu", hl->len, hr->len, ho->len);
+    Op o;
+    o.kind = OpKind::Binary;
+    o.dtype = hl->dtype;
+    o.binop = op;
+    o.arg_ids = {hl->id, hr->id, ho->id};
+    o.in = {hl->id, hr->id};
+    o.out = ho->id;
+    return add_op(d, std::move(o));
+}
+
+// `add_op(&mut out, |out, _| { out.clear(); Ok(()) })` (src/modules/lazy.rs:733-738): a clear that is
+// RECORDED under Lazy, unlike ClearBuf::clear below, which the reference runs eagerly on every stack.
+extern "C" int32_t cbm_clear_op(cbm_device *d, cbm_buf b)
+{
+    CB_CHECK_ARG(d, "null device");
+    GET_HANDLE(h, d, b);
+    Op o;
+    o.kind = OpKind::Clear;
+    o.dtype = h->dtype;
+    o.arg_ids = {h->id};
+    o.out = h->id;
+    return add_op(d, std::move(o));
 }
 
 extern "C" int32_t cbm_clear(cbm_device *d, cbm_buf b)

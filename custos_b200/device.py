@@ -247,8 +247,23 @@ class CUDA:
     def div(self, lhs: Buffer, rhs: Buffer) -> Buffer:
         return self._binary(N.BIN_DIV, lhs, rhs)
 
+    def binary_into(self, op: int, lhs: Buffer, rhs: Buffer, out: Buffer) -> None:
+        """`launch_kernel1d(len, src, "add", &[&lhs, &rhs, &mut out, &len])` of the reference's tests
+        (src/devices/cuda/lazy.rs:96-141): the caller owns `out`; recorded under Lazy."""
+        N.call("cbm_binary_into", self.h, op, lhs.handle, rhs.handle, out.handle)
+
+    def add_into(self, lhs: Buffer, rhs: Buffer, out: Buffer) -> None:
+        self.binary_into(N.BIN_ADD, lhs, rhs, out)
+
+    def mul_into(self, lhs: Buffer, rhs: Buffer, out: Buffer) -> None:
+        self.binary_into(N.BIN_MUL, lhs, rhs, out)
+
     def clear(self, buf: Buffer) -> None:
         buf.clear()
+
+    def clear_op(self, buf: Buffer) -> None:
+        """`add_op(&mut out, |out, _| out.clear())` (src/modules/lazy.rs:733-738): recorded under Lazy."""
+        N.call("cbm_clear_op", self.h, buf.handle)
 
     def copy_slice_to(self, source: Buffer, source_range: range, dest: Buffer, dest_range: range) -> None:
         """CopySlice::copy_slice_to (src/op_traits.rs:34-60)"""
@@ -343,12 +358,35 @@ class CUDA:
     def set_cursor(self, cursor: int) -> None:
         N.call("cbm_set_cursor", self.h, cursor)
 
+    def bump_cursor(self) -> None:
+        """Cursor::bump_cursor (src/features.rs:68-111): what every cached retrieve does."""
+        self.set_cursor(self.cursor() + 1)
+
     def range(self, *args):
-        """device.range(..) (src/range.rs:35-48): every iteration starts at the same cursor."""
+        """device.range(..) (src/range.rs:9-60): the cursor at loop entry is restored at the start of every
+        iteration; after the loop it stays where the last iteration left it.  `range(None)` / `range(a, None)`
+        are the unbounded `..` / `a..` forms."""
         start = self.cursor()
-        for i in range(*args):
+        if len(args) == 1:
+            lo, hi = 0, args[0]
+        else:
+            lo, hi = args[0], args[1]
+        i = lo
+        while hi is None or i < hi:
             self.set_cursor(start)
             yield i
+            i += 1
+
+    def span(self, storage: dict) -> None:
+        """`span!(device, span_storage)` (src/range/span.rs:8-30): the first visit of a call site records the
+        cursor, every later visit of the same site restores it.  The site is the caller's (file, line)."""
+        import sys
+        f = sys._getframe(1)
+        site = (f.f_code.co_filename, f.f_lineno)
+        if site in storage:
+            self.set_cursor(storage[site])
+        else:
+            storage[site] = self.cursor()
 
     # ------------------------------------------------------------ Autograd
     def zero_grad(self) -> None:

@@ -352,7 +352,12 @@ int32_t cbm_unary_ew(cbm_device *d, cbm_buf in, const cb_node *fwd, int32_t n_fw
                      const cb_node *grad, int32_t n_grad, cbm_buf *out);
 /* binary element-wise op with the retrieve + add_op pattern of README.md:96-122 */
 int32_t cbm_binary(cbm_device *d, int32_t op, cbm_buf lhs, cbm_buf rhs, cbm_buf *out);
+/* the same op into a buffer the caller owns (the reference tests' own kernels: `launch_kernel1d(..,
+ * &[&lhs, &rhs, &mut out, &len])`, src/devices/cuda/lazy.rs:96-141): recorded under Lazy, no retrieve */
+int32_t cbm_binary_into(cbm_device *d, int32_t op, cbm_buf lhs, cbm_buf rhs, cbm_buf out);
 int32_t cbm_clear(cbm_device *d, cbm_buf b);                  /* ClearBuf::clear, eager like the reference */
+/* `add_op(&mut out, |out, _| out.clear())` (src/modules/lazy.rs:733-738): a clear that Lazy records */
+int32_t cbm_clear_op(cbm_device *d, cbm_buf b);
 int32_t cbm_copy_slice(cbm_device *d, cbm_buf src, size_t src_off, cbm_buf dst, size_t dst_off, size_t n);
 int32_t cbm_clone_buf(cbm_device *d, cbm_buf src, cbm_buf *out);
 /* sum / mean of a buffer to a host scalar of the accumulation type (executes now) */
