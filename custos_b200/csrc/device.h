@@ -49,6 +49,9 @@ struct Tunables {
     int waves = 16;  // CB_WAVES: grid cap = SMs x resident blocks x waves; >1 lets the hardware rebalance
                      // SMs that run slower (a single static wave left ~10% on the table, profiles/r1_tuning.md)
     int pair = 1;  // CB_PAIR: f32 chains evaluate two elements per thread on the packed f32x2 pipe
+    int tile_redo = 0;  // CB_TILE_REDO=1: one fast-path / fallback decision per tile instead of per 16-byte unit
+                        // (10 % fewer instructions but burstier stores: slower on B200, profiles/r1_tuning.md)
+    int neg_xor = 0;    // CB_NEG_XOR=1: f32 pair neg flips the sign bits on the integer pipe (no gain measured)
     int h_native = 1;  // CB_H_NATIVE: f16 add / sub / mul as single HFMA2s on packed halves
     std::string ld_mod = ".cs";
     std::string st_mod = ".cs";

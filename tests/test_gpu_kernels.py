@@ -269,6 +269,32 @@ def test_apply_in_place_and_unaligned(raw_device):
     dev.free(q)
 
 
+def test_in_place_with_lanes_on_the_slow_path(raw_device):
+    # lanes with |x| > 1e5 leave the packed fast path of sin / cos; their tile is reloaded and redone with the
+    # scalar forms — that must also hold when the kernel runs in place (nothing of the tile is stored before)
+    dev = raw_device
+    rng = np.random.default_rng(14)
+    x = rng.uniform(-4, 4, 300_007).astype(np.float32)
+    x[rng.integers(0, x.size, 2000)] = rng.uniform(-1e6, 1e6, 2000).astype(np.float32)   # scattered slow lanes
+    chain = [lambda v: v.mul(1.5), lambda v: v.sin(), lambda v: v.add(0.25), lambda v: v.cos()]
+    separate = run_apply(dev, chain, N.F32, x)
+    p = dev.upload(x)
+    dev.apply(dev.compile(chain, N.F32), p, p, x.size)
+    in_place = dev.d2h(p, x.size, N.F32)
+    dev.free(p)
+    assert_bit_exact(in_place, separate, "in place == out of place")
+    cur = x
+    for f in chain:  # and both equal the op-by-op device result (every op <= 4 ulp of the oracle on its own input)
+        nxt = run_apply(dev, f, N.F32, cur)
+        lim = 0 if f in (chain[0], chain[2]) else 4
+        (assert_bit_exact if lim == 0 else lambda a, b, w: assert_ulp(a, b, lim, w))(nxt, orc.apply_fn(f, N.F32, cur), "op")
+        cur = nxt
+    assert_bit_exact(separate, cur, "fused == op by op")
+    h = x.astype(np.float16)
+    h[::97] = np.float16(60000.0)  # f16 slow lanes (|x| <= 65504 < 1e5 never leaves the fast path: still exact)
+    assert_bit_exact(run_apply(dev, [lambda v: v.sin()], N.F16, h), run_apply(dev, lambda v: v.sin(), N.F16, h))
+
+
 def test_kernel_cache_reuses_compiled_chain(raw_device):
     e1 = raw_device.compile(CHAIN8, N.F32)
     e2 = raw_device.compile(CHAIN8, N.F32)

@@ -240,3 +240,35 @@ def test_retrieves_in_a_range_reuse_their_allocations():
             seen.add((a.ptr(), b.ptr()))
             assert b.read().tolist() == ((np.arange(8) + 1) * 2).tolist()
         assert len(seen) == 1 and dev.cursor() == 2
+
+
+# ------------------------------------------------------------------ src/modules/autograd.rs
+def test_grad_fn_with_lazy_buffer_source_but_no_true_lazy():
+    # :432-453: Autograd<Lazy<Base>> — a grad fn `buf.grad = 5 * out.grad` runs at backward() although Lazy is on the
+    # stack (backward executes eagerly); seed ones -> [5; 10]
+    with CUDA("Autograd", "Lazy", "Base") as dev:
+        buf = dev.new_buffer(np.float32, 10).require_grad()
+        out = dev.unary_ew(buf, lambda x: x.mul(5.0), lambda x: 5.0)
+        out.backward()
+        assert buf.grad().read().tolist() == [5.0] * 10
+
+
+def test_grad_fn_with_out_of_scope_buffer():
+    # :455-476 (#[should_panic]): the differentiated buffer left its scope before backward()
+    with CUDA("Autograd", "Lazy", "Base") as dev:
+        buf = dev.new_buffer(np.float32, 10).require_grad()
+        out = dev.unary_ew(buf, lambda x: x.mul(5.0), lambda x: 5.0)
+        buf.drop()
+        with pytest.raises(CustosError) as ei:
+            out.backward()
+        assert ei.value.code == N.CB_ERR_INVALID_LAZY_BUF
+
+
+def test_tape_return_with_and_without_autograd():
+    # :425-430 (#[should_panic] without Autograd) and :478-493 (grad() allocates a zeroed gradient on first use)
+    with CUDA("Base") as dev:
+        with pytest.raises(CustosError):
+            dev.new_buffer(np.float32, 10).grad()
+    with CUDA("Autograd", "Base") as dev:
+        buf = dev.new_buffer(np.float32, 10)
+        assert buf.grad().read().tolist() == [0.0] * 10
