@@ -131,6 +131,40 @@ def make_input(n: int, seed: int = 4) -> np.ndarray:
     return out
 
 
+def pcie_ceiling(torch, nbytes: int = 1 << 28, reps: int = 4):
+    """What the host link of this box moves with plain pinned-memory copies — the ceiling of the end-to-end
+    number: H2D alone, D2H alone, and both directions at once (GB/s, CUDA events)."""
+    h_a = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    h_b = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d_a = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    d_b = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    cur = torch.cuda.current_stream()
+
+    def timed(h2d: bool, d2h: bool) -> float:
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        s1.wait_event(e0)
+        s2.wait_event(e0)
+        for _ in range(reps):
+            if h2d:
+                with torch.cuda.stream(s1):
+                    d_a.copy_(h_a, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    h_b.copy_(d_b, non_blocking=True)
+        cur.wait_stream(s1)
+        cur.wait_stream(s2)
+        e1.record()
+        e1.synchronize()
+        return (int(h2d) + int(d2h)) * reps * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+    timed(True, True)  # warm-up
+    return {"h2d_gbs": timed(True, False), "d2h_gbs": timed(False, True), "bidir_gbs": timed(True, True),
+            "how": f"torch pinned copies of {nbytes >> 20} MiB x {reps}, one stream per direction, CUDA events"}
+
+
 def cpu_baseline_single(sample: int):
     """The oracle (kind "port") on ONE host core: the reference CPU device is single threaded."""
     from custos_b200.workloads import CHAIN8
@@ -283,6 +317,13 @@ def run_ours(args):
     barrier()
     e2e_ms = max_over_ranks((te1 - te0) * 1e3) / e2e_steps
     e2e_value = world * n * BYTES_PER_ELEM / (e2e_ms * 1e-3) / 1e9
+    # the ceiling of that number is the host link, not HBM: measure it with plain pinned copies
+    try:
+        barrier()
+        pcie = pcie_ceiling(torch)
+        pcie["e2e_frac_of_bidir"] = (e2e_value / world) / pcie["bidir_gbs"]
+    except Exception as e:  # noqa: BLE001
+        pcie = {"error": repr(e)}
 
     # sanity: the timed kernel really computed the chain (sampled check against the oracle)
     check = None
@@ -308,7 +349,8 @@ def run_ours(args):
                      "kernel": "cb_apply_vec (NVRTC, fused CHAIN8)", "algorithmic_bytes_per_launch": n * BYTES_PER_ELEM},
         "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                 "ms_per_step": e2e_ms, "steps": e2e_steps, "gpu_launches": int(launches_e2e),
-                "api": "cb_apply_host: pinned host buffers, 16 MiB chunks, H2D / kernel / D2H on three streams"},
+                "api": "cb_apply_host: pinned host buffers, 16 MiB chunks, H2D / kernel / D2H on three streams",
+                "host_link": pcie},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "sustained": sustained,
