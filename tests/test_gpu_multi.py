@@ -49,6 +49,21 @@ def _rank(rank: int, world: int, uid: bytes, uid_nccl: bytes, n: int, out_dir: s
     comm.sum_into(N.F32, p, local.size if rank else 0, out)
     part0 = dev.d2h(out, 1, N.F32)[0]
     np.save(f"{out_dir}/p2p{rank}.npy", np.array([1.0 if comm.uses_peer_memory else 0.0, float(part0)]))
+    # other accumulator widths through both exchange paths: f64 (double), bf16 (f32 accumulator), i16 (i64)
+    from custos_b200.expr import bf16_from_f32
+    extra = {}
+    for dt, data in ((N.F64, x.astype(np.float64)), (N.BF16, bf16_from_f32(x)), (N.I16, (x * 30000).astype(np.int16))):
+        loc = np.ascontiguousarray(data[b:e])
+        pd = dev.upload(loc)
+        got = []
+        for c in (comm, comm_nccl):
+            dev.clear(N.U8, out, 64)
+            c.sum_into(dt, pd, loc.size, out)
+            got.append(dev.d2h(out, 8, N.U8).tobytes())
+        assert got[0] == got[1], f"peer-memory and NCCL exchange disagree for dtype {dt}"
+        extra[dt] = got[0]
+        dev.free(pd)
+    np.save(f"{out_dir}/extra{rank}.npy", np.frombuffer(b"".join(extra[k] for k in sorted(extra)), np.uint8))
     comm_nccl.close()
     # element-wise work on the slice: no communication
     q = dev.alloc(local.nbytes)
@@ -91,5 +106,24 @@ def test_sharded_sum_over_nccl(tmp_path, world):
     for p in partials[1:]:
         want_wo0 = np.float32(want_wo0 + p)
     assert all(np.float32(v[1]) == want_wo0 for v in p2p)
+    # the other dtypes: rank-ordered fold of the per-slice oracle partials (floats), exact i64 sum (integers)
+    from custos_b200.expr import bf16_from_f32
+    datas = {N.F64: x.astype(np.float64), N.BF16: bf16_from_f32(x), N.I16: (x * 30000).astype(np.int16)}
+    want_extra = {}
+    for dt, data in datas.items():
+        if dt == N.I16:
+            want_extra[dt] = np.int64(data.astype(np.int64).sum()).tobytes()
+            continue
+        acc = None
+        for r in range(world):
+            b, e = shard_range(n, 4, world, r)  # the ranks slice every dtype at the f32 bounds
+            plan = sum_plan(dt, e - b)
+            part = orc.sum_two_pass(dt, data[b:e], plan["blocks"], plan["chunk"], plan["threads"], plan["vec"], plan["threads2"])
+            acc = part if acc is None else type(part)(acc + part)
+        want_extra[dt] = acc.tobytes().ljust(8, b"\0")
+    for r in range(world):
+        raw = np.load(tmp_path / f"extra{r}.npy").tobytes()
+        for k, dt in enumerate(sorted(datas)):
+            assert raw[8 * k:8 * k + 8] == want_extra[dt], (r, dt)
     full = np.concatenate([np.load(tmp_path / f"out{r}.npy") for r in range(world)])
     assert np.array_equal(full.view(np.uint32), orc.apply_chain(CHEAP8, orc.F32, x).view(np.uint32))
