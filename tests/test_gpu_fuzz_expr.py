@@ -7,6 +7,7 @@ reproduces, and prints the `to_cl_source` string of the offending tree.
 The transcendental ops are left out on purpose: their bar is an ulp bound per function (test_gpu_kernels.py),
 and a composition of them has no meaningful bit-level expectation.
 """
+import os
 import random
 
 import numpy as np
@@ -61,13 +62,16 @@ def ops_for(dt):
     return INT_BIN, (["neg"] if signed else []), INT_LITS
 
 
+# CB_FUZZ_ROUNDS=k repeats every test with k different seed sets (the committed default is one, ~30 s on a B200)
+ROUNDS = int(os.environ.get("CB_FUZZ_ROUNDS", "1"))
 ALL_NUMBERS = [N.F32, N.F64, N.F16, N.BF16, N.I32, N.I64, N.U32, N.U8, N.I8, N.I16, N.U16, N.U64]
 
 
+@pytest.mark.parametrize("rnd", range(ROUNDS))
 @pytest.mark.parametrize("dt", ALL_NUMBERS)
-def test_random_unary_expressions_and_chains(raw_device, dt):
+def test_random_unary_expressions_and_chains(raw_device, dt, rnd):
     dev = raw_device
-    rng = random.Random(1000 + dt)
+    rng = random.Random(1000 + dt + 7919 * rnd)
     bins, uns, lits = ops_for(dt)
     x = inputs_for(dt, 4099, 50 + dt)
     px, po = dev.upload(x), dev.alloc(x.nbytes)
@@ -86,10 +90,11 @@ def test_random_unary_expressions_and_chains(raw_device, dt):
     dev.free(po)
 
 
+@pytest.mark.parametrize("rnd", range(ROUNDS))
 @pytest.mark.parametrize("dt", ALL_NUMBERS)
-def test_random_two_marker_expressions_and_grads(raw_device, dt):
+def test_random_two_marker_expressions_and_grads(raw_device, dt, rnd):
     dev = raw_device
-    rng = random.Random(2000 + dt)
+    rng = random.Random(2000 + dt + 7919 * rnd)
     bins, uns, lits = ops_for(dt)
     x, y = inputs_for(dt, 3001, 60 + dt), inputs_for(dt, 3001, 70 + dt)
     g0 = inputs_for(dt, 3001, 80 + dt)
