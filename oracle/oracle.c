@@ -630,6 +630,38 @@ int orc_sum_two_pass(int dtype, const void *in, size_t len, int blocks, size_t c
     return orc_sum_seq(dtype, in, len, out);
 }
 
+/* ------------------------------------------------------------------ ulp statistics (f32)
+ * Distance in units in the last place between two f32 arrays on the monotonic integer line; NaN vs NaN
+ * counts as 0, NaN vs number as 2^31.  hist[k] counts distances k = 0..4, hist[5] everything above.
+ * Returns the maximum and writes the index of its first occurrence. */
+uint32_t orc_ulp_stats_f32(const float *got, const float *want, size_t n, uint64_t hist[6], size_t *argmax)
+{
+    uint32_t worst = 0;
+    size_t where = 0;
+    for (size_t i = 0; i < n; i++) {
+        uint32_t a, b;
+        memcpy(&a, &got[i], 4);
+        memcpy(&b, &want[i], 4);
+        const int na = (a & 0x7fffffffu) > 0x7f800000u, nb = (b & 0x7fffffffu) > 0x7f800000u;
+        uint32_t d;
+        if (na || nb) {
+            d = (na && nb) ? 0u : 0x80000000u;
+        } else {
+            const int64_t oa = (a & 0x80000000u) ? -(int64_t)(a & 0x7fffffffu) : (int64_t)a;
+            const int64_t ob = (b & 0x80000000u) ? -(int64_t)(b & 0x7fffffffu) : (int64_t)b;
+            const int64_t diff = oa > ob ? oa - ob : ob - oa;
+            d = diff > 0x7fffffff ? 0x7fffffffu : (uint32_t)diff;
+        }
+        hist[d < 5 ? d : 5]++;
+        if (d > worst) {
+            worst = d;
+            where = i;
+        }
+    }
+    if (argmax) *argmax = where;
+    return worst;
+}
+
 /* ------------------------------------------------------------------ OptGraph
  * src/modules/graph/node.rs:2-42, opt_graph.rs:6-41, opt_graph/optimize.rs:19-132 */
 struct orc_gnode {

@@ -43,6 +43,8 @@ size_t orc_dtype_size(int dtype);
 /* half crate 2.x software conversions (round to nearest even) */
 uint16_t orc_f32_to_f16(float v);
 float orc_f16_to_f32(uint16_t h);
+/* ulp distance statistics between two f32 arrays (test helper; see oracle.c) */
+uint32_t orc_ulp_stats_f32(const float *got, const float *want, size_t n, uint64_t hist[6], size_t *argmax);
 uint16_t orc_f32_to_bf16(float v); /* half::bf16::from_f32 */
 float orc_bf16_to_f32(uint16_t h);
 

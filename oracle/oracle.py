@@ -61,6 +61,8 @@ def lib() -> C.CDLL:
         L.orc_sum_seq.argtypes = [i32, vp, sz, vp]
         L.orc_sum_f64.argtypes, L.orc_sum_f64.restype = [i32, vp, sz], C.c_double
         L.orc_sum_two_pass.argtypes = [i32, vp, sz, i32, sz, i32, i32, i32, vp]
+        L.orc_ulp_stats_f32.argtypes = [vp, vp, sz, C.POINTER(C.c_uint64), C.POINTER(sz)]
+        L.orc_ulp_stats_f32.restype = C.c_uint32
         L.orc_graph_new.restype = vp
         L.orc_graph_free.argtypes = [vp]
         L.orc_graph_add_leaf.argtypes, L.orc_graph_add_leaf.restype = [vp, sz], C.c_int64
@@ -179,6 +181,15 @@ def sum_two_pass(dtype, x, blocks, chunk, threads, vec, threads2):
     out = np.zeros(1, ACC_DTYPE[dtype])
     _check(lib().orc_sum_two_pass(dtype, _ptr(x), x.size, blocks, chunk, threads, vec, threads2, _ptr(out)))
     return out[0]
+
+
+def ulp_stats_f32(got: np.ndarray, want: np.ndarray):
+    """-> (max ulp, index of its first occurrence, histogram of distances 0, 1, 2, 3, 4, > 4)"""
+    got, want = np.ascontiguousarray(got, np.float32), np.ascontiguousarray(want, np.float32)
+    hist = (C.c_uint64 * 6)()
+    where = C.c_size_t()
+    worst = lib().orc_ulp_stats_f32(_ptr(got), _ptr(want), got.size, hist, C.byref(where))
+    return int(worst), int(where.value), [int(h) for h in hist]
 
 
 def f32_to_f16_bits(v: float) -> int:
