@@ -175,6 +175,20 @@ def test_transcendental_f16_every_value(raw_device, name):
     assert frac_exact > 0.995, f"f16 {name}: only {frac_exact:.4f} of results identical"
 
 
+def test_signed_zero_goes_through_odd_functions(raw_device):
+    # sin(-0) = tan(-0) = tanh(-0) = -0 and f(+0) = +0, like glibc (and exp(-0) = cos(-0) = 1): the packed forms keep
+    # the sign of a zero through the range reduction and the polynomial
+    z = np.array([0.0, -0.0], np.float32)
+    for dt, x in ((N.F32, z), (N.F64, z.astype(np.float64)), (N.F16, z.astype(np.float16))):
+        for name in ("sin", "tanh", "tan") if dt != N.F16 else ("sin", "tanh"):
+            f = TRANSCENDENTAL[name][0]
+            got = run_apply(raw_device, f, dt, x)
+            assert got.tobytes() == x.tobytes(), (dt, name, got)
+            assert got.tobytes() == orc.apply_fn(f, dt, x).tobytes()
+        for name in ("exp", "cos"):
+            assert run_apply(raw_device, TRANSCENDENTAL[name][0], dt, x).tolist() == [1.0, 1.0]
+
+
 def test_pow_ulp(raw_device):
     rng = np.random.default_rng(23)
     a, b = rng.uniform(0.01, 20, 200_000).astype(np.float32), rng.uniform(-5, 5, 200_000).astype(np.float32)
