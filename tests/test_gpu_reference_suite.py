@@ -245,10 +245,13 @@ def test_retrieves_in_a_range_reuse_their_allocations():
 # ------------------------------------------------------------------ src/modules/autograd.rs
 def test_grad_fn_with_lazy_buffer_source_but_no_true_lazy():
     # :432-453: Autograd<Lazy<Base>> — a grad fn `buf.grad = 5 * out.grad` runs at backward() although Lazy is on the
-    # stack (backward executes eagerly); seed ones -> [5; 10]
+    # stack (backward executes eagerly); seed ones -> [5; 10].  The reference builds `out` with Buffer::new (allocated at
+    # once); here it comes from unary_ew, so the recorded forward op is run first.
     with CUDA("Autograd", "Lazy", "Base") as dev:
         buf = dev.new_buffer(np.float32, 10).require_grad()
         out = dev.unary_ew(buf, lambda x: x.mul(5.0), lambda x: 5.0)
+        dev.run()
+        assert dev.ops_count() == 1  # backward below does not add to, or replay, the recorded forward ops
         out.backward()
         assert buf.grad().read().tolist() == [5.0] * 10
 
@@ -258,6 +261,7 @@ def test_grad_fn_with_out_of_scope_buffer():
     with CUDA("Autograd", "Lazy", "Base") as dev:
         buf = dev.new_buffer(np.float32, 10).require_grad()
         out = dev.unary_ew(buf, lambda x: x.mul(5.0), lambda x: 5.0)
+        dev.run()
         buf.drop()
         with pytest.raises(CustosError) as ei:
             out.backward()
