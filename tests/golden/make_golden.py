@@ -54,6 +54,40 @@ def main():
     out["sum_f64"] = np.array([orc.sum_f64(orc.F32, s)], np.float64)
     np.savez_compressed(Path(__file__).resolve().parent / "oracle_vectors.npz", **out)
     print("wrote", len(out), "arrays")
+    more = dtype_vectors()
+    np.savez_compressed(Path(__file__).resolve().parent / "oracle_vectors_dtypes.npz", **more)
+    print("wrote", len(more), "arrays (bf16 and the narrow / wide integers)")
+
+
+INT_EXPR = lambda v: v.mul(3).add(7).sub(v.div(2))  # noqa: E731
+INT_TYPES = {"i8": (orc.I8, np.int8), "i16": (orc.I16, np.int16), "u16": (orc.U16, np.uint16), "u64": (orc.U64, np.uint64)}
+
+
+def dtype_vectors():
+    """The dtypes added after the first fixture file: bf16 (bit patterns) and i8 / i16 / u16 / u64."""
+    from custos_b200.expr import bf16_from_f32
+    out = {}
+    x = np.random.default_rng(4).uniform(-4, 4, N).astype(np.float32)
+    xb = bf16_from_f32(x)
+    xb[:6] = [0x0000, 0x8000, 0x7f80, 0xff80, 0x7fc0, 0x0001]  # +-0, +-inf, NaN, smallest subnormal
+    out["x_bf16"] = xb
+    out["chain8_y_bf16"] = orc.apply_chain(CHAIN8, orc.BF16, xb)
+    out["cheap8_y_bf16"] = orc.apply_chain(CHEAP8, orc.BF16, xb)
+    yb = bf16_from_f32(np.random.default_rng(3).uniform(-1, 1, N).astype(np.float32))
+    out["y_bf16"] = yb
+    for k, name in enumerate(("add", "mul", "sub", "div")):
+        out[f"binary_{name}_bf16"] = orc.binary(k, orc.BF16, xb, yb)
+    out["max_min_bf16"] = orc.apply2(lambda a, b: a.max(b).min(a.mul(b)), orc.BF16, xb, yb)
+    zeros = np.array([0.0, -0.0, -0.0, 0.0], np.float16)
+    out["max_ties_f16"] = orc.apply2(lambda a, b: a.max(b), orc.F16, zeros, zeros[::-1].copy()).view(np.uint16)
+    for name, (dt, t) in INT_TYPES.items():
+        info = np.iinfo(t)
+        v = np.random.default_rng(7).integers(info.min, min(info.max, 2 ** 62), N, dtype=np.int64).astype(t)
+        v[:4] = [info.min, info.max, 0, 1]
+        out[f"x_{name}"] = v
+        out[f"expr_y_{name}"] = orc.apply_fn(INT_EXPR, dt, v)
+        out[f"sum_{name}"] = np.array([orc.sum_seq(dt, v)], np.int64)
+    return out
 
 
 if __name__ == "__main__":

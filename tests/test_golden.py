@@ -199,3 +199,60 @@ def test_gpu_against_committed_vectors(raw_device):
     assert dev.sum(N.F32, p, 4096) == g["sum_two_pass_f32"][0]
     assert abs(float(dev.sum(N.F32, p, 4096)) - g["sum_f64"][0]) <= 1e-6 * g["sum_f64"][0]
     dev.free(p)
+
+
+# ------------------------------------------------------------------ the dtypes added later (second fixture file)
+def _dtype_cases():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", GOLDEN / "make_golden.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.INT_EXPR, mod.INT_TYPES
+
+
+def test_oracle_reproduces_the_dtype_vectors():
+    g = np.load(GOLDEN / "oracle_vectors_dtypes.npz")
+    xb, yb = g["x_bf16"], g["y_bf16"]
+    assert np.array_equal(orc.apply_chain(CHAIN8, orc.BF16, xb), g["chain8_y_bf16"])
+    assert np.array_equal(orc.apply_chain(CHEAP8, orc.BF16, xb), g["cheap8_y_bf16"])
+    for k, name in enumerate(("add", "mul", "sub", "div")):
+        assert np.array_equal(orc.binary(k, orc.BF16, xb, yb), g[f"binary_{name}_bf16"])
+    assert np.array_equal(orc.apply2(lambda a, b: a.max(b).min(a.mul(b)), orc.BF16, xb, yb), g["max_min_bf16"])
+    assert g["max_ties_f16"].tolist() == [0x0000, 0x8000, 0x8000, 0x0000]  # half's f16::max keeps `self` on +0 / -0 ties
+    expr, types = _dtype_cases()
+    for name, (dt, t) in types.items():
+        assert np.array_equal(orc.apply_fn(expr, dt, g[f"x_{name}"]), g[f"expr_y_{name}"]), name
+        assert orc.sum_seq(dt, g[f"x_{name}"]) == g[f"sum_{name}"][0]
+
+
+@pytest.mark.gpu
+def test_gpu_against_the_dtype_vectors(raw_device):
+    from tests.helpers import assert_bf16_bit_exact, bf16_ulp_distance
+    dev = raw_device
+    g = np.load(GOLDEN / "oracle_vectors_dtypes.npz")
+    xb, yb = g["x_bf16"], g["y_bf16"]
+    assert_bf16_bit_exact(gpu_apply(dev, CHEAP8, N.BF16, xb), g["cheap8_y_bf16"], "cheap8 bf16 vs golden")
+    pa, pb, po = dev.upload(xb), dev.upload(yb), dev.alloc(xb.nbytes)
+    for k, name in enumerate(("add", "mul", "sub", "div")):
+        dev.binary(N.BF16, k, pa, pb, po, xb.size)
+        assert_bf16_bit_exact(dev.d2h(po, xb.size, N.BF16), g[f"binary_{name}_bf16"], f"bf16 {name} vs golden")
+    dev.apply2(dev.compile(lambda a, b: a.max(b).min(a.mul(b)), N.BF16, N.KERNEL_BINARY), pa, pb, po, xb.size)
+    assert_bf16_bit_exact(dev.d2h(po, xb.size, N.BF16), g["max_min_bf16"], "bf16 max/min vs golden")
+    for p in (pa, pb, po):
+        dev.free(p)
+    y = gpu_apply(dev, CHAIN8, N.BF16, xb)
+    assert float(np.mean(y == g["chain8_y_bf16"])) > 0.97  # composition of three transcendentals, each <= 1 ulp(bf16)
+    assert float(np.max(bf16_ulp_distance(y, g["chain8_y_bf16"]))) <= 16
+    zeros = np.array([0.0, -0.0, -0.0, 0.0], np.float16)
+    pz, pr, pq = dev.upload(zeros), dev.upload(zeros[::-1].copy()), dev.alloc(8)
+    dev.apply2(dev.compile(lambda a, b: a.max(b), N.F16, N.KERNEL_BINARY), pz, pr, pq, 4)
+    assert dev.d2h(pq, 4, N.F16).view(np.uint16).tolist() == g["max_ties_f16"].tolist()
+    for p in (pz, pr, pq):
+        dev.free(p)
+    expr, types = _dtype_cases()
+    for name, (dt, t) in types.items():
+        x = g[f"x_{name}"]
+        assert np.array_equal(gpu_apply(dev, expr, dt, x), g[f"expr_y_{name}"]), name
+        p = dev.upload(x)
+        assert dev.sum(dt, p, x.size) == g[f"sum_{name}"][0]
+        dev.free(p)
