@@ -276,3 +276,13 @@ def test_tape_return_with_and_without_autograd():
     with CUDA("Autograd", "Base") as dev:
         buf = dev.new_buffer(np.float32, 10)
         assert buf.grad().read().tolist() == [0.0] * 10
+
+
+# ------------------------------------------------------------------ tests/cuda/scalar_ops.rs
+def test_scalar_op_cuda():
+    # :29-39 `lhs + 3.` on [1..5] and :41-59 `+ 1.` on 0..100000 (a buffer op with a scalar = an apply_fn with a literal)
+    with CUDA("Base") as dev:
+        lhs = dev.buffer(np.array([1., 2., 3., 4., 5.], np.float32))
+        assert dev.apply_fn(lhs, lambda x: x.add(3.0)).read().tolist() == [4., 5., 6., 7., 8.]
+        big = dev.buffer(np.arange(100000, dtype=np.float32))
+        assert np.array_equal(dev.apply_fn(big, lambda x: x.add(1.0)).read(), np.arange(100000, dtype=np.float32) + 1)
