@@ -95,3 +95,35 @@ def test_untyped_type_set_is_astype():
     # src/devices/untyped/matches_type.rs:28-71
     lib = N.load()
     assert [dt for dt in range(13) if lib.cbm_untyped_supports(dt)] == sorted([N.U8, N.U32, N.I64, N.BF16, N.F16, N.F32, N.F64])
+
+
+@pytest.mark.parametrize("dt,np_t", [(N.F32, np.float32), (N.F64, np.float64)])
+def test_float_digits_are_the_shortest_round_trip_digits(dt, np_t):
+    # ryu prints the shortest digit string that reads back to the same float (closest one on ties); NumPy's
+    # `unique=True` formatting implements the same rule independently (Dragon4), so the DIGITS and the decimal
+    # exponent must agree value by value — only the layout (where ryu switches to exponent form) is ours to restate.
+    rng = np.random.default_rng(11)
+    mags = 10.0 ** rng.uniform(-30 if np_t is np.float32 else -250, 30 if np_t is np.float32 else 250, 4000)
+    vals = (rng.standard_normal(4000) * mags).astype(np_t)
+    vals = vals[np.isfinite(vals) & (vals != 0)]
+    text = serde.encode(vals, dt).decode()[1:-1].split(",")
+    assert len(text) == vals.size
+    for s, v in zip(text, vals):
+        want = np.format_float_scientific(v, unique=True, trim="-")          # d.ddde+XX
+        wd, we = want.lstrip("-").split("e")
+        want_digits, want_exp = wd.replace(".", "").rstrip("0") or "0", int(we)
+        body = s.lstrip("-")
+        if "e" in body:
+            m, e = body.split("e")
+            digits = m.replace(".", "")
+            exp10 = int(e)
+        else:
+            ip, fp = body.split(".")
+            if ip.strip("0"):
+                digits, exp10 = (ip + fp), len(ip.lstrip("0")) - 1
+                digits = digits.lstrip("0")
+            else:
+                stripped = fp.lstrip("0")
+                digits, exp10 = stripped, -(len(fp) - len(stripped)) - 1
+        assert digits.rstrip("0") == want_digits and exp10 == want_exp, (s, want)
+        assert s.startswith("-") == bool(v < 0)
