@@ -63,6 +63,10 @@ int32_t expr_validate(int32_t dtype, int32_t kind, const cb_node *nodes, int32_t
             if (op_is_binary(c.op) && (c.b < 0 || c.b >= i))
                 return fail(CB_ERR_EXPR, "node %d: operand b=%d out of order", i, c.b);
         }
+        // unused operand slots must be "none" (negative): every consumer may then index by a / b whenever it is >= 0
+        if (!op_is_binary(c.op) && c.b >= 0) return fail(CB_ERR_EXPR, "node %d: op '%s' takes no operand b (got %d)", i, op_name(c.op), c.b);
+        if (!op_is_binary(c.op) && !op_is_unary(c.op) && c.a >= 0)
+            return fail(CB_ERR_EXPR, "node %d: '%s' is a leaf and takes no operand a (got %d)", i, op_name(c.op), c.a);
         if (c.op == CB_OP_CONST && is_half_dtype(dtype)) {
             if (std::isfinite(c.fimm) && (double)host_half_to_f32(dtype, host_f32_to_half(dtype, (float)c.fimm)) != c.fimm)
                 return fail(CB_ERR_EXPR, "node %d: literal %.17g is not representable in %s (round it first)", i,

@@ -127,11 +127,14 @@ static int check_prog(const orc_node *nd, int n)
     for (int i = 0; i < n; i++) {
         const int op = nd[i].op;
         if (op < 0 || op >= ORC_OP_COUNT) return ORC_ERR_EXPR;
+        const int binary = (op >= ORC_OP_ADD && op <= ORC_OP_MAX) || (op >= ORC_OP_GEQ);
         if (op >= ORC_OP_ADD) {
             if (nd[i].a < 0 || nd[i].a >= i) return ORC_ERR_EXPR;
-            const int binary = (op >= ORC_OP_ADD && op <= ORC_OP_MAX) || (op >= ORC_OP_GEQ);
             if (binary && (nd[i].b < 0 || nd[i].b >= i)) return ORC_ERR_EXPR;
         }
+        /* unused operand slots must be negative: the evaluators index by a / b whenever it is >= 0 */
+        if (!binary && nd[i].b >= 0) return ORC_ERR_EXPR;
+        if (op < ORC_OP_ADD && nd[i].a >= 0) return ORC_ERR_EXPR;
     }
     return ORC_OK;
 }
