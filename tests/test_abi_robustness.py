@@ -117,3 +117,35 @@ def test_small_output_buffers_and_nulls():
     assert lib.cb_serde_decode(N.I32, N.SER_BINCODE, b"\x01", 1, None, 0, C.byref(sz)) == N.CB_ERR_PARSE
     assert lib.cb_shard_range(10, 4, 0, 0, C.byref(sz), C.byref(sz)) != N.CB_OK
     assert lib.cb_shard_range(10, 4, 2, 5, C.byref(sz), C.byref(sz)) != N.CB_OK
+
+
+def test_optgraph_api_with_garbage_arguments():
+    """Out-of-range node indices, negative counts, null / undersized output arrays: error codes, no memory errors."""
+    lib = N.load()
+    rng = random.Random(1)
+    for _ in range(200):
+        g = C.c_void_p()
+        assert lib.cb_optgraph_create(C.byref(g)) == N.CB_OK
+        n = 0
+        for _ in range(rng.randint(0, 12)):
+            idx = C.c_int64()
+            if rng.random() < 0.3:
+                rc = lib.cb_optgraph_add_leaf(g, rng.choice([0, 1, 10, 2 ** 40]), C.byref(idx))
+            else:
+                k = rng.randint(0, 4)
+                deps = (C.c_int64 * max(k, 1))(*[rng.randint(-3, n + 3) for _ in range(k)])
+                rc = lib.cb_optgraph_add_node(g, rng.choice([0, 1, 10]), deps, rng.choice([k, k, -1, 0]), C.byref(idx))
+            if rc == N.CB_OK:
+                assert idx.value == n
+                n += 1
+        out, w, flag = (C.c_int64 * 256)(), C.c_size_t(), C.c_int32()
+        for q in range(-2, n + 3):
+            rc = lib.cb_optgraph_is_path_optimizable(g, q, C.byref(flag))
+            assert (rc == N.CB_OK) == (0 <= q < n)
+            rc = lib.cb_optgraph_trace_cache_path_raw(g, q, out, rng.choice([0, 1, 256]), C.byref(w))
+            assert rc == N.CB_OK or not 0 <= q < n or w.value > 0
+            assert (lib.cb_optgraph_set_skip(g, q, 1) == N.CB_OK) == (0 <= q < n)
+        lib.cb_optgraph_cache_traces(g, out, rng.choice([0, 3, 256]), C.byref(w))
+        lib.cb_optgraph_cache_traces(g, None, 0, C.byref(w))
+        assert lib.cb_optgraph_destroy(g) == N.CB_OK
+    assert lib.cb_optgraph_destroy(None) in (N.CB_OK, N.CB_ERR_INVALID_ARG)
