@@ -148,6 +148,31 @@ struct Parser {
     }
 };
 
+// the JSON number grammar: -?(0|[1-9][0-9]*)(\.[0-9]+)?([eE][+-]?[0-9]+)?
+bool json_number(const std::string &t)
+{
+    size_t i = 0;
+    const size_t n = t.size();
+    auto digits = [&]() {
+        const size_t start = i;
+        while (i < n && t[i] >= '0' && t[i] <= '9') i++;
+        return i - start;
+    };
+    if (i < n && t[i] == '-') i++;
+    if (i < n && t[i] == '0') i++;
+    else if (!digits()) return false;
+    if (i < n && t[i] == '.') {
+        i++;
+        if (!digits()) return false;
+    }
+    if (i < n && (t[i] == 'e' || t[i] == 'E')) {
+        i++;
+        if (i < n && (t[i] == '+' || t[i] == '-')) i++;
+        if (!digits()) return false;
+    }
+    return i == n;
+}
+
 // one JSON scalar into the element at `dst`; false on a token that serde_json would reject for this type
 bool parse_element(Parser &ps, int32_t dtype, unsigned char *dst)
 {
@@ -160,15 +185,17 @@ bool parse_element(Parser &ps, int32_t dtype, unsigned char *dst)
     }
     const char *tok = ps.p;
     const char *q = tok;
-    while (q < ps.end && (std::strchr("+-.eE", *q) || (*q >= '0' && *q <= '9'))) q++;
+    auto number_char = [](char ch) { return (ch >= '0' && ch <= '9') || ch == '+' || ch == '-' || ch == '.' || ch == 'e' || ch == 'E'; };
+    while (q < ps.end && number_char(*q)) q++;
     if (q == tok) return false;  // includes `null`: not a number
     const std::string text(tok, q);
+    if (!json_number(text)) return false;  // "+1", "01", "1.", ".5", "1e" are not JSON
     ps.p = q;
     char *stop = nullptr;
     errno = 0;
     if (dtype == CB_F32 || dtype == CB_F64) {
         const double v = std::strtod(text.c_str(), &stop);  // serde_json parses to f64; f32 is `as f32`
-        if (*stop) return false;
+        if (*stop || (errno == ERANGE && std::isinf(v))) return false;  // serde_json: "number out of range"
         if (dtype == CB_F64) std::memcpy(dst, &v, 8);
         else { const float f = (float)v; std::memcpy(dst, &f, 4); }
         return true;

@@ -127,3 +127,46 @@ def test_float_digits_are_the_shortest_round_trip_digits(dt, np_t):
                 digits, exp10 = stripped, -(len(fp) - len(stripped)) - 1
         assert digits.rstrip("0") == want_digits and exp10 == want_exp, (s, want)
         assert s.startswith("-") == bool(v < 0)
+
+
+def test_decoder_survives_arbitrary_bytes():
+    """The decoder parses untrusted bytes: random garbage and mutated valid documents either decode or fail with
+    CB_ERR_PARSE (run under ASan / UBSan by scripts/host_sanitize.sh)."""
+    import random
+    rng = random.Random(7)
+    valid = [serde.encode(np.arange(-3, 4, dtype=np.int32), N.I32), serde.encode(np.array([1.5, -2e-7, 3e30], np.float32), N.F32),
+             serde.encode(np.array([True, False]), N.BOOL), serde.encode(np.arange(5, dtype=np.uint8), N.U8, serde.BINCODE),
+             serde.encode(np.array([1.0, 2.0]), N.F64, serde.BINCODE)]
+    dtypes = [N.I8, N.U8, N.I16, N.U16, N.I32, N.U32, N.I64, N.U64, N.F32, N.F64, N.BOOL]
+    outcomes = {"ok": 0, "parse": 0}
+    for _ in range(6000):
+        doc = bytearray(rng.choice(valid))
+        for _ in range(rng.randint(0, 4)):
+            roll = rng.random()
+            if roll < 0.4 and doc:
+                doc[rng.randrange(len(doc))] = rng.randrange(256)
+            elif roll < 0.7:
+                doc.insert(rng.randrange(len(doc) + 1), rng.choice(b"[],.-+eE0123456789 \x00tf\"{}n"))
+            elif doc:
+                del doc[rng.randrange(len(doc))]
+        if rng.random() < 0.1:
+            doc = bytearray(rng.randbytes(rng.randint(0, 40)))
+        for fmt in (serde.JSON, serde.BINCODE):
+            dt = rng.choice(dtypes)
+            try:
+                out = serde.decode(bytes(doc), dt, fmt)
+                outcomes["ok"] += 1
+                assert out.dtype == np.dtype({N.BOOL: np.bool_}.get(dt, out.dtype))
+            except CustosError as e:
+                assert e.code == N.CB_ERR_PARSE, (bytes(doc), dt, fmt, e)
+                outcomes["parse"] += 1
+    assert outcomes["ok"] > 200 and outcomes["parse"] > 2000
+    with pytest.raises(CustosError):
+        serde.decode(b"[1\x00]", N.I32)  # a NUL is not part of a number
+    # the JSON number grammar, as serde_json enforces it
+    for ok in (b"[1]", b"[-0]", b"[0.5]", b"[1e5]", b"[1E-5]", b"[-1.25e+3]", b"[1e-999]"):
+        serde.decode(ok, N.F64)
+    for bad in (b"[+1]", b"[01]", b"[1.]", b"[.5]", b"[1e]", b"[--1]", b"[1e999]", b"[0x10]", b"[1_0]", b"[1,,2]", b"[Infinity]", b"[NaN]"):
+        with pytest.raises(CustosError) as ei:
+            serde.decode(bad, N.F64)
+        assert ei.value.code == N.CB_ERR_PARSE, bad
