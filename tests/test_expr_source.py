@@ -127,3 +127,28 @@ def test_literals_round_to_the_dtype():
     assert arr[1].fimm == float(np.float16(0.1))
     arr, n = E.flatten(lambda x: x.mul(0.1), N.F32)
     assert arr[1].fimm == float(np.float32(0.1))
+
+
+@pytest.mark.parametrize("dt,np_t", [(N.F32, np.float32), (N.F64, np.float64)])
+def test_literal_formatting_is_rusts_debug_on_random_values(dt, np_t):
+    # Rust `{:?}` of a float (library/core/src/fmt/float.rs): the shortest digits that read back to the same value, in
+    # decimal notation with at least one fractional digit when 1e-4 <= |v| < 1e16 (or v == 0), otherwise `d.ddde<exp>`.
+    # NumPy's unique (Dragon4) formatting yields the same digits independently.
+    rng = np.random.default_rng(21)
+    span = 36 if np_t is np.float32 else 300
+    vals = (rng.standard_normal(1500) * 10.0 ** rng.uniform(-span, span, 1500)).astype(np_t)
+    vals = np.concatenate([vals[np.isfinite(vals) & (vals != 0)], np.array([1e-4, 9.999e-5, 1e16, 9.99e15, 1.0, 0.1, 123456.0], np_t)])
+    for v in vals:
+        src = E.to_cl_source(lambda x: x.add(v), dt)
+        assert src.startswith("(x + ") and src.endswith(")")
+        lit = src[5:-1]
+        sci = np.format_float_scientific(v, unique=True, trim="-")
+        digits, exp = sci.lstrip("-").split("e")
+        digits, exp = digits.replace(".", "").rstrip("0") or "0", int(exp)
+        if 1e-4 <= abs(float(v)) < 1e16:
+            want = np.format_float_positional(v, unique=True, trim="0")
+            want = want + "0" if want.endswith(".") else want
+        else:
+            want = ("-" if v < 0 else "") + digits[0] + ("." + digits[1:] if len(digits) > 1 else "") + f"e{exp}"
+        assert lit == want, (float(v), lit, want)
+        assert np_t(lit) == v  # and it reads back to the same value
