@@ -61,7 +61,8 @@ def run_program(dev, steps, inputs, prepare=None, runs=1):
     if prepare:
         prepare(dev)
     for _ in range(runs):
-        dev.run() if "Lazy" in dev.modules else None
+        if "Lazy" in dev.modules:
+            dev.run()
     sinks = [i for i in range(len(bufs)) if i not in consumed]
     return {i: bufs[i].replace().read() for i in sinks}
 
@@ -76,6 +77,10 @@ CONFIGS = {
     "elementwise_fusing": (("Graph", "Lazy", "Base"), lambda d: d.elementwise_fusing(), 1),
     "elementwise_fusing+replay": (("Graph", "Lazy", "Base"), lambda d: (d.elementwise_fusing(), d.set_graph_replay(True)), 3),
     "replay": (("Lazy", "Base"), lambda d: d.set_graph_replay(True), 3),
+    "graph_lazy_cached+mem_graph": (("Graph", "Lazy", "Cached", "Base"), lambda d: d.optimize_mem_graph(), 2),
+    "autograd_lazy": (("Autograd", "Lazy", "Base"), None, 1),
+    "autograd_graph_lazy+unary_fusing": (("Autograd", "Graph", "Lazy", "Base"), lambda d: d.unary_fusing(), 1),
+    "cached": (("Cached", "Base"), None, 1),
 }
 
 
