@@ -302,8 +302,130 @@ static const char *cuda_fn(int32_t op)
     }
 }
 
+// right-hand side of one node of the f32 pair function
+static std::string pair_rhs(const cb_node &c, const std::string &ta, const std::string &tb)
+{
+    if (c.op == CB_OP_X) return "x";
+    if (c.op == CB_OP_Y) return "y";
+    if (c.op == CB_OP_CONST) return "cb2_splat(" + cuda_literal(CB_F32, c) + ")";
+    const std::string name = "cb2_" + std::string(cuda_fn(c.op) + 3);
+    if (op_is_binary(c.op)) return name + "(" + ta + ", " + tb + ")";
+    if (c.op == CB_OP_SIN || c.op == CB_OP_COS) return name + "(" + ta + ", redo)";  // fast path only; `redo` asks for the scalar forms
+    return name + "(" + ta + ")";
+}
+
+// |v| = 2^k with k >= min_k (and finite): multiplying by it is exact apart from overflow / underflow
+static bool is_pow2(double v, int min_k, int *k_out)
+{
+    if (!std::isfinite(v) || v == 0.0) return false;
+    int e = 0;
+    const double m = std::frexp(std::fabs(v), &e);  // |v| = m * 2^e, m in [0.5, 1)
+    if (m != 0.5) return false;
+    if (e - 1 < min_k) return false;
+    if (k_out) *k_out = e - 1;
+    return true;
+}
+
+// The f32 pair function of a whole chain with scale-and-shift steps strength-reduced to ONE fma, bit for bit:
+//   A.  (u * P) + C  ->  fma(u, P, C)       P = +-2^k, k >= 0: u * P is exact (or overflows, and then both forms give
+//                                            the same infinity because |C| <= 2^100 cannot bring the sum back)
+//   B.  (u + C) * P  ->  fma(u, P, C * P)   P = +-2^k, any k: scaling by a power of two commutes with rounding as long
+//                                            as the result is normal, zero or overflows; a non-zero u + C is at least
+//                                            2^(e_C - 24) in magnitude, so e_C - 24 + k >= -126 keeps it normal
+// The chain is first joined into one tree (the marker of op k+1 is the value of op k), so a `mul(2.0)` op followed by
+// an `add(1.0)` op fuses as well.  Only the pair function is rewritten: the scalar `cb_fn` (tails, unaligned
+// buffers, the slow-path redo) keeps the two separately rounded operations, which makes every test that compares the
+// vector path with the scalar path a check of the equivalence claimed here.
+static std::string fused_pair_function(const cb_node *const *progs, const int32_t *n_nodes, int32_t n_progs)
+{
+    std::vector<cb_node> all;
+    int32_t prev_root = -1;
+    for (int32_t k = 0; k < n_progs; k++) {
+        std::vector<int32_t> map((size_t)n_nodes[k], -1);
+        for (int32_t i = 0; i < n_nodes[k]; i++) {
+            cb_node c = progs[k][i];
+            if (c.op == CB_OP_X && prev_root >= 0) {
+                map[(size_t)i] = prev_root;
+                continue;
+            }
+            if (c.a >= 0) c.a = map[(size_t)c.a];
+            if (c.b >= 0) c.b = map[(size_t)c.b];
+            map[(size_t)i] = (int32_t)all.size();
+            all.push_back(c);
+        }
+        prev_root = map[(size_t)n_nodes[k] - 1];
+    }
+    const int32_t n = (int32_t)all.size();
+    std::vector<int> uses((size_t)n, 0);
+    for (const cb_node &c : all) {
+        if (c.a >= 0) uses[(size_t)c.a]++;
+        if (c.b >= 0) uses[(size_t)c.b]++;
+    }
+    uses[(size_t)prev_root]++;
+    auto lit = [&all](int32_t i, double *v) {
+        if (i < 0 || all[(size_t)i].op != CB_OP_CONST) return false;
+        *v = (double)(float)all[(size_t)i].fimm;
+        return true;
+    };
+    auto literal_text = [](double v) {
+        cb_node c;
+        std::memset(&c, 0, sizeof c);
+        c.op = CB_OP_CONST;
+        c.fimm = v;
+        return "cb2_splat(" + cuda_literal(CB_F32, c) + ")";
+    };
+    std::vector<char> absorbed((size_t)n, 0);
+    std::vector<std::string> rhs((size_t)n);
+    for (int32_t i = 0; i < n; i++) {
+        const cb_node &c = all[(size_t)i];
+        rhs[(size_t)i] = pair_rhs(c, "t" + std::to_string(c.a), "t" + std::to_string(c.b));
+        if (c.op != CB_OP_ADD && c.op != CB_OP_MUL) continue;
+        for (int side = 0; side < 2; side++) {
+            const int32_t inner = side ? c.b : c.a, other = side ? c.a : c.b;
+            double outer_lit;
+            if (!lit(other, &outer_lit) || uses[(size_t)inner] != 1) continue;
+            const cb_node &in = all[(size_t)inner];
+            if (in.op != (c.op == CB_OP_ADD ? CB_OP_MUL : CB_OP_ADD)) continue;
+            for (int iside = 0; iside < 2; iside++) {
+                const int32_t u = iside ? in.b : in.a, ilit = iside ? in.a : in.b;
+                double inner_lit;
+                if (!lit(ilit, &inner_lit) || all[(size_t)u].op == CB_OP_CONST) continue;
+                double P, C, addend;
+                int k = 0;
+                if (c.op == CB_OP_ADD) {  // A: (u * P) + C
+                    P = inner_lit, C = outer_lit;
+                    if (!is_pow2(P, 0, &k) || !std::isfinite(C) || std::fabs(C) > 0x1p100) continue;
+                    addend = C;
+                } else {  // B: (u + C) * P
+                    P = outer_lit, C = inner_lit;
+                    int ec = 0;
+                    if (!is_pow2(P, -200, &k) || !std::isfinite(C) || C == 0.0) continue;
+                    std::frexp(C, &ec);  // |C| in [2^(ec-1), 2^ec)
+                    addend = C * P;
+                    if ((ec - 1) - 24 + k < -126 || !std::isfinite(addend) || (double)(float)addend != addend ||
+                        std::fabs(addend) < 0x1p-126)
+                        continue;
+                }
+                rhs[(size_t)i] = "cb2_fmap(t" + std::to_string(u) + ", " + literal_text(P) + ", " + literal_text(addend) + ")";
+                absorbed[(size_t)inner] = 1;
+                side = 2;
+                break;
+            }
+        }
+    }
+    // literals that only fed an absorbed node are dead; the compiler drops them
+    std::string s = "#if CB_PAIR\n__device__ __forceinline__ cb_f2 cb_fn2(cb_f2 x, cb_f2 y, bool &redo)\n{\n";
+    s += "    const cb_f2 x_in = x;\n    (void)x_in;\n";
+    for (int32_t i = 0; i < n; i++) {
+        if (absorbed[(size_t)i]) continue;
+        s += "    const cb_f2 t" + std::to_string(i) + " = " + rhs[(size_t)i] + ";\n";
+    }
+    s += "    return t" + std::to_string(prev_root) + ";\n}\n#endif\n";
+    return s;
+}
+
 std::string expr_cuda_function(int32_t dtype, const cb_node *const *progs, const int32_t *n_nodes,
-                               int32_t n_progs)
+                               int32_t n_progs, bool fuse_scale_add)
 {
     std::string s;
     s += "// generated from the recorded Combiner trees; one block per recorded op, applied in order\n";
@@ -328,7 +450,9 @@ std::string expr_cuda_function(int32_t dtype, const cb_node *const *progs, const
         s += "        x = t" + std::to_string(n - 1) + ";\n    }\n";
     }
     s += "    return x;\n}\n";
-    if (dtype == CB_F32) {
+    if (dtype == CB_F32 && fuse_scale_add) {
+        s += fused_pair_function(progs, n_nodes, n_progs);
+    } else if (dtype == CB_F32) {
         // the same programs on two elements at a time (one f32x2 register pair, see skeleton.cuh)
         s += "#if CB_PAIR\n__device__ __forceinline__ cb_f2 cb_fn2(cb_f2 x, cb_f2 y, bool &redo)\n{\n";
         for (int32_t k = 0; k < n_progs; k++) {
@@ -337,17 +461,7 @@ std::string expr_cuda_function(int32_t dtype, const cb_node *const *progs, const
             s += "    { // op " + std::to_string(k) + "\n";
             for (int32_t i = 0; i < n; i++) {
                 const cb_node &c = nd[i];
-                std::string rhs;
-                if (c.op == CB_OP_X) rhs = "x";
-                else if (c.op == CB_OP_Y) rhs = "y";
-                else if (c.op == CB_OP_CONST) rhs = "cb2_splat(" + cuda_literal(dtype, c) + ")";
-                else if (op_is_binary(c.op))
-                    rhs = "cb2_" + std::string(cuda_fn(c.op) + 3) + "(t" + std::to_string(c.a) + ", t" + std::to_string(c.b) + ")";
-                else if (c.op == CB_OP_SIN || c.op == CB_OP_COS)  // fast path only; `redo` asks for the scalar forms
-                    rhs = "cb2_" + std::string(cuda_fn(c.op) + 3) + "(t" + std::to_string(c.a) + ", redo)";
-                else
-                    rhs = "cb2_" + std::string(cuda_fn(c.op) + 3) + "(t" + std::to_string(c.a) + ")";
-                s += "        const cb_f2 t" + std::to_string(i) + " = " + rhs + ";\n";
+                s += "        const cb_f2 t" + std::to_string(i) + " = " + pair_rhs(c, "t" + std::to_string(c.a), "t" + std::to_string(c.b)) + ";\n";
             }
             s += "        x = t" + std::to_string(n - 1) + ";\n    }\n";
         }

@@ -29,7 +29,8 @@ std::string expr_to_cl_source(int32_t dtype, const cb_node *nodes, int32_t n, co
 
 // The generated part of the translation unit: `cb_fn(x, y)` applying the programs in order.
 std::string expr_cuda_function(int32_t dtype, const cb_node *const *progs, const int32_t *n_nodes,
-                               int32_t n_progs);
+                               int32_t n_progs,
+                               bool fuse_scale_add = false);
 
 // 64-bit key of (dtype, kind, programs) for the kernel cache
 // canonical byte string of (dtype, kind, programs): what chain_hash hashes, kept to confirm cache hits
