@@ -52,7 +52,7 @@ struct Tunables {
     int tile_redo = 0;  // CB_TILE_REDO=1: one fast-path / fallback decision per tile instead of per 16-byte unit
                         // (10 % fewer instructions but burstier stores: slower on B200, profiles/r1_tuning.md)
     int neg_xor = 0;    // CB_NEG_XOR=1: f32 pair neg flips the sign bits on the integer pipe (no gain measured)
-    int fuse_scale_add = 0;  // CB_FUSE_SCALE_ADD=1: (u * 2^k) + C and (u + C) * 2^k become one exact fma in the f32 pair path
+    int fuse_scale_add = 1;  // CB_FUSE_SCALE_ADD: (u * 2^k) + C and (u + C) * 2^k become one exact fma in the f32 pair path
     int h_native = 1;  // CB_H_NATIVE: f16 add / sub / mul as single HFMA2s on packed halves
     std::string ld_mod = ".cs";
     std::string st_mod = ".cs";
