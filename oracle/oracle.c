@@ -665,6 +665,81 @@ uint32_t orc_ulp_stats_f32(const float *got, const float *want, size_t n, uint64
     return worst;
 }
 
+/* ------------------------------------------------------------------ scale-and-shift equivalence (f32)
+ * Checks, over the f32 bit patterns [first, first + count), that two separately rounded operations equal ONE fused
+ * multiply-add (glibc fmaf, correctly rounded) bit for bit (NaN == NaN):
+ *   mode 0:  (u * P) + C  ==  fmaf(u, P, C)
+ *   mode 1:  (u + C) * P  ==  fmaf(u, P, C * P)
+ * Returns the number of mismatches and writes the first offending pattern.  This is the machine check of the
+ * strength reduction in custos_b200/csrc/expr.cpp (fused_pair_function); built with -ffp-contract=off, so the
+ * left-hand sides really round twice. */
+struct sa_job {
+    uint64_t first, count;
+    float P, C;
+    int mode;
+    uint64_t bad;
+    uint32_t first_bad;
+};
+
+static void *sa_worker(void *arg)
+{
+    struct sa_job *j = (struct sa_job *)arg;
+    const float P = j->P, C = j->C, CP = C * P;
+    for (uint64_t k = 0; k < j->count; k++) {
+        const uint32_t bits = (uint32_t)(j->first + k);
+        float u;
+        memcpy(&u, &bits, 4);
+        volatile float two_step;
+        float fused;
+        if (j->mode == 0) {
+            volatile float t = u * P;
+            two_step = t + C;
+            fused = fmaf(u, P, C);
+        } else {
+            volatile float t = u + C;
+            two_step = t * P;
+            fused = fmaf(u, P, CP);
+        }
+        const float a = two_step;
+        uint32_t x, y;
+        memcpy(&x, &a, 4);
+        memcpy(&y, &fused, 4);
+        const int nx = (x & 0x7fffffffu) > 0x7f800000u, ny = (y & 0x7fffffffu) > 0x7f800000u;
+        if ((nx || ny) ? (nx != ny) : (x != y)) {
+            if (!j->bad) j->first_bad = bits;
+            j->bad++;
+        }
+    }
+    return NULL;
+}
+
+uint64_t orc_check_scale_add(uint64_t first, uint64_t count, float P, float C, int mode, int threads, uint32_t *first_bad)
+{
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    pthread_t tid[256];
+    struct sa_job jobs[256];
+    const uint64_t per = (count + (uint64_t)threads - 1) / (uint64_t)threads;
+    int started = 0;
+    for (int t = 0; t < threads; t++) {
+        const uint64_t b = per * (uint64_t)t;
+        if (b >= count) break;
+        jobs[t] = (struct sa_job){first + b, (b + per > count) ? count - b : per, P, C, mode, 0, 0};
+        if (pthread_create(&tid[t], NULL, sa_worker, &jobs[t]) != 0) {
+            sa_worker(&jobs[t]);
+            tid[t] = 0;
+        }
+        started = t + 1;
+    }
+    uint64_t bad = 0;
+    for (int t = 0; t < started; t++) {
+        if (tid[t]) pthread_join(tid[t], NULL);
+        if (jobs[t].bad && !bad && first_bad) *first_bad = jobs[t].first_bad;
+        bad += jobs[t].bad;
+    }
+    return bad;
+}
+
 /* ------------------------------------------------------------------ OptGraph
  * src/modules/graph/node.rs:2-42, opt_graph.rs:6-41, opt_graph/optimize.rs:19-132 */
 struct orc_gnode {

@@ -63,6 +63,8 @@ def lib() -> C.CDLL:
         L.orc_sum_two_pass.argtypes = [i32, vp, sz, i32, sz, i32, i32, i32, vp]
         L.orc_ulp_stats_f32.argtypes = [vp, vp, sz, C.POINTER(C.c_uint64), C.POINTER(sz)]
         L.orc_ulp_stats_f32.restype = C.c_uint32
+        L.orc_check_scale_add.argtypes = [C.c_uint64, C.c_uint64, C.c_float, C.c_float, i32, i32, C.POINTER(C.c_uint32)]
+        L.orc_check_scale_add.restype = C.c_uint64
         L.orc_graph_new.restype = vp
         L.orc_graph_free.argtypes = [vp]
         L.orc_graph_add_leaf.argtypes, L.orc_graph_add_leaf.restype = [vp, sz], C.c_int64
@@ -190,6 +192,15 @@ def ulp_stats_f32(got: np.ndarray, want: np.ndarray):
     where = C.c_size_t()
     worst = lib().orc_ulp_stats_f32(_ptr(got), _ptr(want), got.size, hist, C.byref(where))
     return int(worst), int(where.value), [int(h) for h in hist]
+
+
+def check_scale_add(P: float, Cc: float, mode: int, first: int = 0, count: int = 1 << 32, threads: int = 0):
+    """Mismatches between two rounded steps and one fmaf over f32 bit patterns [first, first + count); mode 0:
+    (u * P) + C, mode 1: (u + C) * P.  -> (number of mismatches, first offending bit pattern)"""
+    import os
+    first_bad = C.c_uint32(0)
+    bad = lib().orc_check_scale_add(first, count, P, Cc, mode, threads or (os.cpu_count() or 1), C.byref(first_bad))
+    return int(bad), int(first_bad.value)
 
 
 def f32_to_f16_bits(v: float) -> int:
