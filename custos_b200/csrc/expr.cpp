@@ -374,7 +374,7 @@ static std::string fused_pair_function(const cb_node *const *progs, const int32_
         c.fimm = v;
         return "cb2_splat(" + cuda_literal(CB_F32, c) + ")";
     };
-    std::vector<char> absorbed((size_t)n, 0);
+    std::vector<char> absorbed((size_t)n, 0), rewritten((size_t)n, 0);  // rewritten: already the outer node of a fused pair
     std::vector<std::string> rhs((size_t)n);
     for (int32_t i = 0; i < n; i++) {
         const cb_node &c = all[(size_t)i];
@@ -383,7 +383,7 @@ static std::string fused_pair_function(const cb_node *const *progs, const int32_
         for (int side = 0; side < 2; side++) {
             const int32_t inner = side ? c.b : c.a, other = side ? c.a : c.b;
             double outer_lit;
-            if (!lit(other, &outer_lit) || uses[(size_t)inner] != 1) continue;
+            if (!lit(other, &outer_lit) || uses[(size_t)inner] != 1 || rewritten[(size_t)inner]) continue;
             const cb_node &in = all[(size_t)inner];
             if (in.op != (c.op == CB_OP_ADD ? CB_OP_MUL : CB_OP_ADD)) continue;
             for (int iside = 0; iside < 2; iside++) {
@@ -408,6 +408,7 @@ static std::string fused_pair_function(const cb_node *const *progs, const int32_
                 }
                 rhs[(size_t)i] = "cb2_fmap(t" + std::to_string(u) + ", " + literal_text(P) + ", " + literal_text(addend) + ")";
                 absorbed[(size_t)inner] = 1;
+                rewritten[(size_t)i] = 1;
                 side = 2;
                 break;
             }

@@ -83,6 +83,33 @@ def test_a_shared_inner_node_is_not_absorbed():
     assert fmas(body) == [] and body.count("cb2_mul(") == 2 and body.count("cb2_add(") == 1
 
 
+def test_nested_patterns_fuse_once_and_still_compile():
+    # ((x + 1) * 2) + 3: the inner pair becomes fma(x, 2, 2); the outer add must then stay an add of that value
+    for f, n_fma, n_add, n_mul in ((lambda x: x.add(1.0).mul(2.0).add(3.0), 1, 1, 0),
+                                   (lambda x: x.mul(2.0).add(1.0).mul(4.0), 1, 0, 1),
+                                   (lambda x: x.mul(2.0).add(1.0).mul(4.0).add(0.5).mul(x), 2, 0, 1),
+                                   (lambda x: x.add(1.0).mul(2.0).add(x.mul(4.0).add(2.0)), 2, 1, 0)):
+        body = pair_function(f)
+        assert (len(fmas(body)), body.count("cb2_add("), body.count("cb2_mul(")) == (n_fma, n_add, n_mul), body
+        assert E.compile_check([f], N.F32) > 1000
+        assert E.compile_check([f], N.F32, N.KERNEL_UNARY_GRAD) > 1000
+
+
+def test_random_trees_still_compile_with_the_fusion_on():
+    import random
+    from custos_b200.expr import Combiner, Resolve
+    rng = random.Random(5)
+    lits = [0.5, 2.0, -1.5, 3.0, 0.25, 1.0, -0.0, 8.0, -0.75, 4.0]
+
+    def tree(depth):
+        if depth == 0 or rng.random() < 0.2:
+            return Resolve("x") if rng.random() < 0.6 else Combiner._wrap(rng.choice(lits))
+        a, b = tree(depth - 1), tree(depth - 1)
+        return getattr(a, rng.choice(["add", "mul", "add", "mul", "sub"]))(b)
+    for _ in range(25):
+        assert E.compile_check([tree(rng.randint(2, 5))], N.F32) > 1000
+
+
 def test_fusion_across_recorded_ops_and_in_the_other_kernel_kinds():
     assert len(fmas(pair_function([lambda x: x.sin(), lambda x: x.mul(4.0), lambda x: x.add(0.5), lambda x: x.cos()]))) == 1
     assert len(fmas(pair_function(lambda x: x.mul(2.0).add(1.0), kind=N.KERNEL_UNARY_GRAD))) == 1
