@@ -329,9 +329,12 @@ static bool is_pow2(double v, int min_k, int *k_out)
 // The f32 pair function of a whole chain with scale-and-shift steps strength-reduced to ONE fma, bit for bit:
 //   A.  (u * P) + C  ->  fma(u, P, C)       P = +-2^k, k >= 0: u * P is exact (or overflows, and then both forms give
 //                                            the same infinity because |C| <= 2^100 cannot bring the sum back)
-//   B.  (u + C) * P  ->  fma(u, P, C * P)   P = +-2^k, any k: scaling by a power of two commutes with rounding as long
+//   B.  (u + C) * P  ->  fma(u, P, C * P)   P = +2^k, any k: scaling by a power of two commutes with rounding as long
 //                                            as the result is normal, zero or overflows; a non-zero u + C is at least
-//                                            2^(e_C - 24) in magnitude, so e_C - 24 + k >= -126 keeps it normal
+//                                            2^(e_C - 24) in magnitude, so e_C - 24 + k >= -126 keeps it normal;
+//                                            |C| <= 2^100 keeps u + C itself from overflowing, and P must be positive
+//                                            because u = -C gives (+0) * P = -0 for a negative P but +0 when fused
+// (the last two conditions were found by tests/test_scale_add_fusion.py, which interprets the generated text on the CPU)
 // The chain is first joined into one tree (the marker of op k+1 is the value of op k), so a `mul(2.0)` op followed by
 // an `add(1.0)` op fuses as well.  Only the pair function is rewritten: the scalar `cb_fn` (tails, unaligned
 // buffers, the slow-path redo) keeps the two separately rounded operations, which makes every test that compares the
@@ -399,7 +402,9 @@ static std::string fused_pair_function(const cb_node *const *progs, const int32_
                 } else {  // B: (u + C) * P
                     P = outer_lit, C = inner_lit;
                     int ec = 0;
-                    if (!is_pow2(P, -200, &k) || !std::isfinite(C) || C == 0.0) continue;
+                    // P > 0: for u = -C the sum is +0 and (+0) * P keeps the sign of P, while the fused form gives +0;
+                    // |C| <= 2^100: u + C must not overflow where the scaled-down result would be finite
+                    if (!is_pow2(P, -200, &k) || P < 0.0 || !std::isfinite(C) || C == 0.0 || std::fabs(C) > 0x1p100) continue;
                     std::frexp(C, &ec);  // |C| in [2^(ec-1), 2^ec)
                     addend = C * P;
                     if ((ec - 1) - 24 + k < -126 || !std::isfinite(addend) || (double)(float)addend != addend ||

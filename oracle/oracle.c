@@ -713,6 +713,12 @@ static void *sa_worker(void *arg)
     return NULL;
 }
 
+/* out[i] = fmaf(a[i], b, c): glibc's correctly rounded fused multiply-add, element by element */
+void orc_fmaf_array(const float *a, float b, float c, float *out, size_t n)
+{
+    for (size_t i = 0; i < n; i++) out[i] = fmaf(a[i], b, c);
+}
+
 uint64_t orc_check_scale_add(uint64_t first, uint64_t count, float P, float C, int mode, int threads, uint32_t *first_bad)
 {
     if (threads < 1) threads = 1;

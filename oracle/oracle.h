@@ -46,6 +46,7 @@ float orc_f16_to_f32(uint16_t h);
 /* ulp distance statistics between two f32 arrays (test helper; see oracle.c) */
 uint32_t orc_ulp_stats_f32(const float *got, const float *want, size_t n, uint64_t hist[6], size_t *argmax);
 /* (u * P) + C == fmaf(u, P, C) [mode 0] / (u + C) * P == fmaf(u, P, C * P) [mode 1] over a range of f32 bit patterns */
+void orc_fmaf_array(const float *a, float b, float c, float *out, size_t n);
 uint64_t orc_check_scale_add(uint64_t first, uint64_t count, float P, float C, int mode, int threads, uint32_t *first_bad);
 uint16_t orc_f32_to_bf16(float v); /* half::bf16::from_f32 */
 float orc_bf16_to_f32(uint16_t h);

@@ -63,6 +63,7 @@ def lib() -> C.CDLL:
         L.orc_sum_two_pass.argtypes = [i32, vp, sz, i32, sz, i32, i32, i32, vp]
         L.orc_ulp_stats_f32.argtypes = [vp, vp, sz, C.POINTER(C.c_uint64), C.POINTER(sz)]
         L.orc_ulp_stats_f32.restype = C.c_uint32
+        L.orc_fmaf_array.argtypes, L.orc_fmaf_array.restype = [vp, C.c_float, C.c_float, vp, sz], None
         L.orc_check_scale_add.argtypes = [C.c_uint64, C.c_uint64, C.c_float, C.c_float, i32, i32, C.POINTER(C.c_uint32)]
         L.orc_check_scale_add.restype = C.c_uint64
         L.orc_graph_new.restype = vp
@@ -192,6 +193,14 @@ def ulp_stats_f32(got: np.ndarray, want: np.ndarray):
     where = C.c_size_t()
     worst = lib().orc_ulp_stats_f32(_ptr(got), _ptr(want), got.size, hist, C.byref(where))
     return int(worst), int(where.value), [int(h) for h in hist]
+
+
+def fmaf_array(a: np.ndarray, b: float, c: float) -> np.ndarray:
+    """fmaf(a[i], b, c) with glibc's correctly rounded fmaf"""
+    a = np.ascontiguousarray(a, np.float32)
+    out = np.empty_like(a)
+    lib().orc_fmaf_array(_ptr(a), b, c, _ptr(out), a.size)
+    return out
 
 
 def check_scale_add(P: float, Cc: float, mode: int, first: int = 0, count: int = 1 << 32, threads: int = 0):

@@ -5,6 +5,8 @@ Two halves, both on the CPU: (1) which expressions the generator rewrites into o
 one fused multiply-add give the same bits — and that the check does find mismatches where the generator refuses."""
 import re
 
+import numpy as np
+
 import pytest
 
 from custos_b200 import _native as N
@@ -55,6 +57,8 @@ NOT_FUSED = {
     "(x+1e-30)*0.125 (one binade too far: 2^-127 is possible)": lambda x: x.add(1e-30).mul(0.125),
     "x*2+1e35 (the addend could undo an overflow)": lambda x: x.mul(2.0).add(1e35),
     "(x+0)*2": lambda x: x.add(0.0).mul(2.0),
+    "(x+1)*-2 (x = -1 gives -0 in two steps, +0 fused)": lambda x: x.add(1.0).mul(-2.0),
+    "(x+1e35)*2^-80 (x + 1e35 can overflow although the scaled result is finite)": lambda x: x.add(1e35).mul(2.0 ** -80),
     "x*x+1": lambda x: x.mul(x).add(1.0),
 }
 
@@ -143,3 +147,105 @@ def test_the_check_finds_the_cases_the_generator_refuses():
     assert orc.check_scale_add(3.0, 1.0, 0, 0x32000000, 1 << 24)[0] > 0                        # not a power of two
     assert orc.check_scale_add(2.0 ** -80, 1e-30, 1, 0x80000000, 1 << 20)[0] > 0               # (x + C) * P lands in the subnormals
     assert orc.check_scale_add(2.0, float.fromhex("0x1p127"), 0, 0xFEF00000, 1 << 21)[0] > 0   # the addend brings an overflowed product back
+    assert orc.check_scale_add(-2.0, 1.0, 1, 0xBF800000, 1) == (1, 0xBF800000)                 # (x + 1) * -2 at x = -1: -0 vs +0
+    assert orc.check_scale_add(2.0 ** -80, 1e35, 1, 0x7f000000, 1 << 23)[0] > 0                # x + 1e35 overflows first
+
+
+# ------------------------------------------------------------------ the generated pair function, interpreted on the CPU
+def interpret_pair_function(body: str, x: np.ndarray, y: np.ndarray | None = None) -> np.ndarray:
+    """Executes the straight-line `cb_fn2` text the generator emitted, in NumPy f32 (every IEEE op rounds once, like the
+    device intrinsics; the fused multiply-adds go through glibc's fmaf).  Exact ops only."""
+    import struct
+    env = {"x": x, "y": y}
+
+    def lit(bits):
+        return np.float32(struct.unpack("<f", struct.pack("<I", int(bits, 16)))[0])
+
+    def value(tok):
+        tok = tok.strip()
+        m = re.fullmatch(r"cb2_splat\(__uint_as_float\(0x([0-9a-f]{8})u\)\)", tok)
+        return lit(m.group(1)) if m else env[tok]
+
+    one = np.float32(1.0)
+    ops2 = {"add": lambda a, b: a + b, "mul": lambda a, b: a * b, "sub": lambda a, b: a - b, "div": lambda a, b: a / b,
+            "min": lambda a, b: np.where(a < b, a, b), "max": lambda a, b: np.where(a > b, a, b),
+            "geq": lambda a, b: np.where(a >= b, one, np.float32(0)), "leq": lambda a, b: np.where(a <= b, one, np.float32(0)),
+            "eq": lambda a, b: np.where(a <= b, one, np.float32(0))}
+    ops1 = {"neg": lambda a: -a, "abs": np.abs, "identity": lambda a: a}
+    result = None
+    with np.errstate(all="ignore"):
+        for line in body.splitlines():
+            m = re.match(r"\s*const cb_f2 (\w+) = (.*);$", line)
+            if not m:
+                r = re.match(r"\s*return (\w+);", line)
+                if r:
+                    result = env[r.group(1)]
+                continue
+            name, rhs = m.group(1), m.group(2)
+            if name == "x_in":
+                continue
+            f = re.fullmatch(r"cb2_fmap\((\w+), (cb2_splat\(.*?\)\)), (cb2_splat\(.*?\)\))\)", rhs)
+            c = re.fullmatch(r"cb2_(\w+)\((.*)\)", rhs)
+            if f:
+                env[name] = orc.fmaf_array(np.broadcast_to(env[f.group(1)], x.shape), float(value(f.group(2))), float(value(f.group(3))))
+            elif rhs.startswith("cb2_splat("):
+                env[name] = value(rhs)
+            elif rhs in ("x", "y"):
+                env[name] = env[rhs]
+            elif c and c.group(1) in ops2:
+                a, b = c.group(2).split(", ")
+                env[name] = np.asarray(ops2[c.group(1)](np.asarray(env[a], np.float32), np.asarray(env[b], np.float32)), np.float32)
+            elif c and c.group(1) in ops1:
+                env[name] = np.asarray(ops1[c.group(1)](np.asarray(env[c.group(2)], np.float32)), np.float32)
+            else:
+                raise AssertionError(f"cannot interpret: {line}")
+    return np.broadcast_to(np.asarray(result, np.float32), x.shape).copy()
+
+
+@pytest.mark.parametrize("seed", [9, 10, 11, 12])
+def test_generated_pair_function_equals_the_oracle_on_random_trees(seed, cases=1200):
+    """What the GPU fuzzer checks on the device, checked here on the generated text: thousands of random exact-op trees
+    (nested scale-and-shift patterns included), evaluated from the emitted `cb_fn2` and by the oracle from the IR."""
+    import random
+    from custos_b200.expr import Combiner, Resolve
+    from tests.helpers import assert_bit_exact, edge_values
+    rng = random.Random(seed)
+    lits = [0.5, 2.0, -1.5, 3.0, 0.25, 1.0, -0.0, 8.0, -0.75, 4.0, 1e-30, 0.125, 2.0 ** -80, 1e35, 2.0 ** 100, -2.0, -0.5, 0.0,
+            2.0 ** 127, 1e-45, 2.0 ** -126, -4.0, 16.0]
+    bins = ["add", "mul", "add", "mul", "sub", "div", "min", "max", "geq", "leq", "eq"]
+    data = np.random.default_rng(3)
+    x = np.concatenate([data.uniform(-4, 4, 600).astype(np.float32), edge_values(np.float32),
+                        np.array([1e-45, -1e-45, 3e-39, -3e-39, 1.7e38, -1.7e38, 3.4e38, -3.4e38, 2e-38, 1e-30 * 0.99], np.float32)])
+    y = data.permutation(x)
+
+    def tree(depth, leaves):
+        roll = rng.random()
+        if depth == 0 or roll < 0.15:
+            return rng.choice(leaves) if rng.random() < 0.65 else Combiner._wrap(rng.choice(lits))
+        if roll < 0.25:
+            return getattr(tree(depth - 1, leaves), rng.choice(["neg", "abs", "identity"]))()
+        if roll < 0.5:  # a scale-and-shift step around a sub-tree: the shapes the rewrite looks for (and must refuse)
+            u, p, c = tree(depth - 1, leaves), Combiner._wrap(rng.choice(lits)), Combiner._wrap(rng.choice(lits))
+            form = rng.randrange(4)
+            return (u.mul(p).add(c), c.add(p.mul(u)), u.add(c).mul(p), p.mul(c.add(u)))[form]
+        a = tree(depth - 1, leaves)
+        return getattr(a, rng.choice(bins))(a if rng.random() < 0.1 else tree(depth - 1, leaves))
+    fused_seen = 0
+    for case in range(cases):
+        two = case % 3 == 0
+        leaves = [Resolve("x"), Resolve("y")] if two else [Resolve("x")]
+        if case % 5 == 4:  # a chain of recorded ops
+            fs = [tree(rng.randint(1, 3), [Resolve("x")]) for _ in range(rng.randint(2, 4))]
+            body, want = pair_function(fs), orc.apply_chain(fs, orc.F32, x)
+            got = interpret_pair_function(body, x)
+        elif two:
+            f = tree(rng.randint(1, 5), leaves)
+            body, want = pair_function(f, 2, N.KERNEL_BINARY), orc.apply2(f, orc.F32, x, y)
+            got = interpret_pair_function(body, x, y)
+        else:
+            f = tree(rng.randint(1, 5), leaves)
+            body, want = pair_function(f), orc.apply_fn(f, orc.F32, x)
+            got = interpret_pair_function(body, x)
+        fused_seen += len(fmas(body))
+        assert_bit_exact(got, want, f"case {case}: {body}")
+    assert fused_seen > cases // 12  # the rewrite really is exercised
