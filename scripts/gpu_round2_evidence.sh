@@ -15,3 +15,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:cb_apply_vec -s 5 -c 1 -o gpurun_out/prof_chain8_fused -f python bench.py --steps 3 --warmup 3 > gpurun_out/ncu_fused.log 2>&1
 python scripts/bench_configs.py > gpurun_out/configs.json 2> gpurun_out/configs.err
 wc -l gpurun_out/launches.csv; ls -la gpurun_out/*.ncu-rep
+# host-side ASan/UBSan WITH a device: the module layer (handles, ids, aliasing, fusing) under the module tests and fuzz
+python -m custos_b200.build --sanitize > gpurun_out/asan_build.log 2>&1
+ASAN=$(gcc -print-file-name=libasan.so); UBSAN=$(gcc -print-file-name=libubsan.so)
+LD_PRELOAD="$ASAN:$UBSAN" ASAN_OPTIONS=detect_leaks=0:protect_shadow_gap=0:halt_on_error=1 UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 \
+  CUSTOS_B200_LIB=custos_b200/lib/libcustos_b200_asan.so \
+  python -m pytest tests/test_gpu_modules.py tests/test_gpu_fuzz_modules.py tests/test_gpu_reference_suite.py tests/test_gpu_untyped.py -m gpu -q -p no:cacheprovider > gpurun_out/asan_gpu.log 2>&1
+tail -3 gpurun_out/asan_gpu.log
