@@ -33,7 +33,8 @@ CB_ERR_INVALID_LAZY_BUF, CB_ERR_MISSING_CACHE_TRACES, CB_ERR_GRAPH_OPTIMIZATION 
 CB_ERR_SHAPE, CB_ERR_STATE, CB_ERR_TYPE_MISMATCH, CB_ERR_PARSE = 9, 10, 11, 12
 SER_JSON, SER_BINCODE = 0, 1
 F32, F64, F16, I32, I64, U32, U8, BF16, I8, I16, U16, U64, BOOL = range(13)
-KERNEL_APPLY, KERNEL_UNARY_GRAD, KERNEL_BINARY = 0, 1, 2
+KERNEL_APPLY, KERNEL_UNARY_GRAD, KERNEL_BINARY, KERNEL_CHAIN_GRAD = 0, 1, 2, 3
+GRAD_SEED_ONES = 1
 BIN_ADD, BIN_MUL, BIN_SUB, BIN_DIV = 0, 1, 2, 3
 CBM_BASE, CBM_CACHED, CBM_LAZY, CBM_GRAPH, CBM_AUTOGRAD = 0, 1, 2, 4, 8
 COMM_ID_BYTES = 128
@@ -73,6 +74,7 @@ SIGNATURES = {
     "cb_expr_release": [_vp],
     "cb_apply": [_vp, _vp, _u64, _u64, _sz],
     "cb_unary_grad": [_vp, _vp, _u64, _u64, _u64, _sz],
+    "cb_unary_grad_ex": [_vp, _vp, _u64, _u64, _u64, _sz, _u32],
     "cb_apply2": [_vp, _vp, _u64, _u64, _u64, _sz],
     "cb_apply_host": [_vp, _vp, _vp, _vp, _sz],
     "cb_binary": [_vp, _i32, _i32, _u64, _u64, _u64, _sz],

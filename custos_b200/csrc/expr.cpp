@@ -9,9 +9,11 @@
 //    semantics of the CPU `Eval` impls, which are the parity target.
 #include "expr.h"
 
+#include <array>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 
 namespace cb {
 
@@ -81,12 +83,18 @@ int32_t expr_validate(int32_t dtype, int32_t kind, const cb_node *nodes, int32_t
 int32_t chain_validate(int32_t dtype, int32_t kind, const cb_node *const *progs, const int32_t *n_nodes,
                        int32_t n_progs)
 {
-    if (kind < CB_KERNEL_APPLY || kind > CB_KERNEL_BINARY) return fail(CB_ERR_INVALID_ARG, "invalid kernel kind %d", kind);
+    if (kind < CB_KERNEL_APPLY || kind > CB_KERNEL_CHAIN_GRAD) return fail(CB_ERR_INVALID_ARG, "invalid kernel kind %d", kind);
     if (!progs || !n_nodes || n_progs <= 0) return fail(CB_ERR_EXPR, "no programs");
-    if (kind != CB_KERNEL_APPLY && n_progs != 1)
-        return fail(CB_ERR_EXPR, "only apply kernels take a chain of programs");
-    if (n_progs > 64) return fail(CB_ERR_EXPR, "chain of %d programs (max 64)", n_progs);
-    for (int32_t k = 0; k < n_progs; k++) CB_TRY(expr_validate(dtype, kind, progs[k], n_nodes[k]));
+    if (kind != CB_KERNEL_APPLY && kind != CB_KERNEL_CHAIN_GRAD && n_progs != 1)
+        return fail(CB_ERR_EXPR, "only apply and chain-grad kernels take a chain of programs");
+    if (kind == CB_KERNEL_CHAIN_GRAD && (n_progs % 2) != 0)
+        return fail(CB_ERR_EXPR, "a chain-grad kernel takes K forward programs followed by their K grad programs (got %d)", n_progs);
+    if (n_progs > 128 || (kind == CB_KERNEL_APPLY && n_progs > 64)) return fail(CB_ERR_EXPR, "chain of %d programs (max 64)", n_progs);
+    // the programs of a chain-grad kernel are unary closures (one marker), like the ops of a fused chain
+    const int32_t prog_kind = kind == CB_KERNEL_CHAIN_GRAD ? CB_KERNEL_APPLY : kind;
+    for (int32_t k = 0; k < n_progs; k++) CB_TRY(expr_validate(dtype, prog_kind, progs[k], n_nodes[k]));
+    if (kind == CB_KERNEL_CHAIN_GRAD && chain_grad_tree(progs, n_nodes, n_progs, true).size() > (size_t)kMaxNodes * 4)
+        return fail(CB_ERR_EXPR, "chain-grad expression too large");
     return CB_OK;
 }
 
@@ -302,6 +310,123 @@ static const char *cuda_fn(int32_t op)
     }
 }
 
+
+// ------------------------------------------------------------------ joined trees (hash-consed)
+// Several programs joined into ONE tree: the marker of a program is the value of an earlier root.  Identical
+// nodes (same op, same operands, same literal) are shared, so `exp(x)` computed by the forward op and again by its
+// grad closure, or `tanh(x)` twice inside `1 - tanh(x) * tanh(x)`, is evaluated once.  Every op is a pure function
+// of its operands, so sharing never changes a result.
+namespace {
+struct Dag {
+    std::vector<cb_node> nodes;
+    std::map<std::array<uint64_t, 5>, int32_t> index;
+    int32_t add(cb_node c)
+    {
+        uint64_t fbits;
+        std::memcpy(&fbits, &c.fimm, 8);
+        if (c.op != CB_OP_CONST) {
+            fbits = 0;
+            c.fimm = 0.0;
+            c.iimm = 0;
+        }
+        c._pad = 0;
+        const std::array<uint64_t, 5> key = {(uint64_t)(uint32_t)c.op, (uint64_t)(uint32_t)c.a, (uint64_t)(uint32_t)c.b, fbits,
+                                             (uint64_t)c.iimm};
+        auto it = index.find(key);
+        if (it != index.end()) return it->second;
+        nodes.push_back(c);
+        index.emplace(key, (int32_t)nodes.size() - 1);
+        return (int32_t)nodes.size() - 1;
+    }
+    int32_t leaf(int32_t op, double f = 0.0, int64_t i = 0)
+    {
+        cb_node c;
+        std::memset(&c, 0, sizeof c);
+        c.op = op;
+        c.a = c.b = -1;
+        c.fimm = f;
+        c.iimm = i;
+        return add(c);
+    }
+    int32_t binary(int32_t op, int32_t a, int32_t b)
+    {
+        cb_node c;
+        std::memset(&c, 0, sizeof c);
+        c.op = op;
+        c.a = a;
+        c.b = b;
+        return add(c);
+    }
+    // appends a unary program whose marker X is the node `x_root`; returns the index of its value
+    int32_t append(const cb_node *prog, int32_t n, int32_t x_root)
+    {
+        std::vector<int32_t> map((size_t)n, -1);
+        for (int32_t i = 0; i < n; i++) {
+            cb_node c = prog[i];
+            if (c.op == CB_OP_X) {
+                map[(size_t)i] = x_root;
+                continue;
+            }
+            if (c.a >= 0) c.a = map[(size_t)c.a];
+            if (c.b >= 0) c.b = map[(size_t)c.b];
+            map[(size_t)i] = add(c);
+        }
+        return map[(size_t)n - 1];
+    }
+    // the nodes `root` depends on, in topological order, re-indexed
+    std::vector<cb_node> reachable(int32_t root) const
+    {
+        std::vector<char> keep(nodes.size(), 0);
+        keep[(size_t)root] = 1;
+        for (int32_t i = root; i >= 0; i--) {
+            if (!keep[(size_t)i]) continue;
+            if (nodes[(size_t)i].a >= 0) keep[(size_t)nodes[(size_t)i].a] = 1;
+            if (nodes[(size_t)i].b >= 0) keep[(size_t)nodes[(size_t)i].b] = 1;
+        }
+        std::vector<int32_t> idx(nodes.size(), -1);
+        std::vector<cb_node> out;
+        for (int32_t i = 0; i <= root; i++) {
+            if (!keep[(size_t)i]) continue;
+            cb_node c = nodes[(size_t)i];
+            if (c.a >= 0) c.a = idx[(size_t)c.a];
+            if (c.b >= 0) c.b = idx[(size_t)c.b];
+            idx[(size_t)i] = (int32_t)out.size();
+            out.push_back(c);
+        }
+        return out;
+    }
+};
+}  // namespace
+
+// The backward of a fused unary chain as ONE two-marker expression (X = the chain's input x0, Y = out_grad[i]):
+// what the K grad functions of `unary_ew` (src/unary.rs:118-128) accumulate into x0's gradient when the tape
+// replays them in reverse (src/modules/autograd/tape.rs:39-47), with every intermediate recomputed from x0:
+//     x_k = f_k(x_{k-1})                                   k = 1 .. K-1      (forward, in registers)
+//     t_K = Y;   t_{k-1} = 0 + t_k * g_k(x_{k-1})          k = K .. 2        (`lhs_grad += out_grad * g(lhs)` into
+//                                                                             a zero-initialised gradient buffer,
+//                                                                             src/devices/cpu_stack_ops.rs:18-30)
+//     value = t_1 * g_1(x_0)                                                  (the kernel adds it to x0.grad)
+// Multiply and add stay separately rounded operations in exactly this order, so the result is bit-identical to the
+// K unfused `add_unary_grad` kernels.  `0 + v` only turns a -0 product into +0; `canon_all = false` keeps that add
+// for t_1 only: a zero stays a zero (of either sign) through every later multiply by a finite factor and becomes a
+// NaN in both forms for an infinite one, so canonicalising once, before the last multiply, gives the same bits
+// (NaN payloads are not preserved by either form).
+std::vector<cb_node> chain_grad_tree(const cb_node *const *progs, const int32_t *n_nodes, int32_t n_progs, bool canon_all)
+{
+    const int32_t K = n_progs / 2;
+    Dag dag;
+    std::vector<int32_t> xs((size_t)K, -1);
+    xs[0] = dag.leaf(CB_OP_X);
+    for (int32_t k = 1; k < K; k++) xs[(size_t)k] = dag.append(progs[k - 1], n_nodes[k - 1], xs[(size_t)k - 1]);
+    int32_t t = dag.leaf(CB_OP_Y);
+    for (int32_t k = K; k >= 1; k--) {
+        const int32_t g = dag.append(progs[K + k - 1], n_nodes[K + k - 1], xs[(size_t)k - 1]);
+        t = dag.binary(CB_OP_MUL, t, g);
+        if (k > 1 && (canon_all || k == 2)) t = dag.binary(CB_OP_ADD, dag.leaf(CB_OP_CONST, 0.0, 0), t);
+    }
+    return dag.reachable(t);
+}
+
 // right-hand side of one node of the f32 pair function
 static std::string pair_rhs(const cb_node &c, const std::string &ta, const std::string &tb)
 {
@@ -419,6 +544,19 @@ static std::string fused_pair_function(const cb_node *const *progs, const int32_
             }
         }
     }
+    // u * 1.0 is u for every u (a NaN stays a NaN; payloads are not preserved anywhere): the constant grad closures
+    // of `add` ops (`|_| 1.0`) cost nothing in a chain-grad kernel.  Done last, so that `(u * 1.0) + C` above still
+    // becomes one fma.
+    for (int32_t i = 0; i < n; i++) {
+        const cb_node &c = all[(size_t)i];
+        if (c.op != CB_OP_MUL || absorbed[(size_t)i] || rewritten[(size_t)i]) continue;
+        double one;
+        const bool a_one = lit(c.a, &one) && one == 1.0, b_one = lit(c.b, &one) && one == 1.0;
+        if (!a_one && !b_one) continue;
+        const int32_t other = b_one ? c.a : c.b;
+        if (all[(size_t)other].op == CB_OP_CONST || absorbed[(size_t)other]) continue;
+        rhs[(size_t)i] = "cb2_identity(t" + std::to_string(other) + ")";
+    }
     // literals that only fed an absorbed node are dead; the compiler drops them
     std::string s = "#if CB_PAIR\n__device__ __forceinline__ cb_f2 cb_fn2(cb_f2 x, cb_f2 y, bool &redo)\n{\n";
     s += "    const cb_f2 x_in = x;\n    (void)x_in;\n";
@@ -430,16 +568,43 @@ static std::string fused_pair_function(const cb_node *const *progs, const int32_
     return s;
 }
 
-std::string expr_cuda_function(int32_t dtype, const cb_node *const *progs, const int32_t *n_nodes,
+std::string expr_cuda_function(int32_t dtype, int32_t kind, const cb_node *const *progs, const int32_t *n_nodes,
                                int32_t n_progs, bool fuse_scale_add)
 {
+    if (kind == CB_KERNEL_CHAIN_GRAD) {
+        // the scalar function (tails, unaligned buffers, the slow-path redo, every dtype but f32) adds the zero of the
+        // intermediate gradient buffer after EVERY op; the f32 pair function only before the last multiply (see
+        // chain_grad_tree) — tests that compare the vector path with the scalar one check that the two agree
+        const std::vector<cb_node> full = chain_grad_tree(progs, n_nodes, n_progs, true);
+        const cb_node *p1[1] = {full.data()};
+        const int32_t c1[1] = {(int32_t)full.size()};
+        std::string out = expr_cuda_function(dtype, CB_KERNEL_BINARY, p1, c1, 1, false);
+        if (dtype == CB_F32) {
+            const std::vector<cb_node> lean = chain_grad_tree(progs, n_nodes, n_progs, !fuse_scale_add);
+            const cb_node *p2[1] = {lean.data()};
+            const int32_t c2[1] = {(int32_t)lean.size()};
+            const size_t cut = out.find("#if CB_PAIR");
+            const size_t end = out.rfind("}  // namespace CB_NS");
+            if (cut != std::string::npos && end != std::string::npos) {
+                std::string pair = fuse_scale_add ? fused_pair_function(p2, c2, 1)
+                                                  : expr_cuda_function(dtype, CB_KERNEL_BINARY, p2, c2, 1, false);
+                if (!fuse_scale_add) {
+                    const size_t a = pair.find("#if CB_PAIR"), b = pair.rfind("}  // namespace CB_NS");
+                    pair = pair.substr(a, b - a);
+                }
+                out = out.substr(0, cut) + pair + out.substr(end);
+            }
+        }
+        return out;
+    }
     std::string s;
     s += "// generated from the recorded Combiner trees; one block per recorded op, applied in order\n";
     s += "namespace CB_NS {\n__device__ __forceinline__ T cb_fn(T x, T y)\n{\n";
     for (int32_t k = 0; k < n_progs; k++) {
         const cb_node *nd = progs[k];
         const int32_t n = n_nodes[k];
-        s += "    { // op " + std::to_string(k) + ": x = " + expr_to_cl_source(dtype, nd, n, "x", "y") + "\n";
+        // (the rendered source of a joined tree with shared nodes can be huge: only small programs get the comment)
+        s += "    { // op " + std::to_string(k) + ": x = " + (n <= 32 ? expr_to_cl_source(dtype, nd, n, "x", "y") : std::to_string(n) + " nodes") + "\n";
         for (int32_t i = 0; i < n; i++) {
             const cb_node &c = nd[i];
             const std::string name = "t" + std::to_string(i);

@@ -28,9 +28,13 @@ std::string expr_to_cl_source(int32_t dtype, const cb_node *nodes, int32_t n, co
                               const char *marker_y);
 
 // The generated part of the translation unit: `cb_fn(x, y)` applying the programs in order.
-std::string expr_cuda_function(int32_t dtype, const cb_node *const *progs, const int32_t *n_nodes,
+std::string expr_cuda_function(int32_t dtype, int32_t kind, const cb_node *const *progs, const int32_t *n_nodes,
                                int32_t n_progs,
                                bool fuse_scale_add = false);
+
+// CB_KERNEL_CHAIN_GRAD: K forward programs + K grad programs joined into the one two-marker expression
+// (X = chain input, Y = out_grad) whose value the kernel adds to the input's gradient; see expr.cpp
+std::vector<cb_node> chain_grad_tree(const cb_node *const *progs, const int32_t *n_nodes, int32_t n_progs, bool canon_all);
 
 // 64-bit key of (dtype, kind, programs) for the kernel cache
 // canonical byte string of (dtype, kind, programs): what chain_hash hashes, kept to confirm cache hits

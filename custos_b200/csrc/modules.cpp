@@ -29,6 +29,16 @@
 //     the trace alone (the reference turns a trace that contains a non-unary op into no-ops,
 //     lazy/optimization.rs:77-91); on pure unary traces — all the reference tests — both agree.
 //   * aliasing / fusing skip buffers whose dtype or length differ instead of panicking later.
+//   * Autograd + fusing / aliasing.  In the reference, `unary_ew` records grad functions that read the INPUT
+//     buffer of every op (src/unary.rs:118-128) while unary fusing turns the ops writing those buffers into no-ops
+//     (lazy/optimization.rs:77-91) and optimize_mem_graph lets them share one allocation (lazy/optimization.rs:4-44):
+//     backward() then reads zeros / overwritten values and returns wrong gradients without an error.  Here both
+//     passes look at the tape first (tape_plan_for_chain): when the K grad functions of a chain are on the tape they
+//     are replaced by ONE chain-grad kernel that recomputes every intermediate from the chain's input
+//     (CB_KERNEL_CHAIN_GRAD: same roundings in the same order as the K add_unary_grad calls, with the
+//     intermediate gradients — which no longer have a buffer worth the name — taken as zero-initialised); when
+//     only part of the chain is on the tape the pass leaves that chain alone.  Forward + backward of a fused
+//     chain is then 2 kernels whatever K is.
 #include <algorithm>
 #include <cstring>
 #include <functional>
@@ -127,7 +137,10 @@ std::vector<cb_node> substitute(const std::vector<cb_node> &outer, int32_t which
 struct GradOp {
     uint64_t buf_id = 0, out_id = 0;
     int32_t dtype = CB_F32;
-    cb_expr *grad_expr = nullptr;
+    cb_expr *grad_expr = nullptr;            // CB_KERNEL_UNARY_GRAD, or CB_KERNEL_CHAIN_GRAD when `chain`
+    std::vector<cb_node> fwd_ir, grad_ir;    // the two closures of unary_ew, kept so that a chain can be fused later
+    bool chain = false;                      // replaces the K grad functions of a fused chain buf_id -> ... -> out_id
+    size_t chain_len = 1;
 };
 
 struct Deferred {
@@ -228,7 +241,7 @@ void on_new_buffer(cbm_device *d, const Handle &h)
         d->graph.add_leaf(h.len);
     }
     d->buffers[h.id] = Entry{h.ptr, h.len, h.dtype};
-    if (d->has(CBM_AUTOGRAD)) d->requires_grad.emplace(h.id, false);
+    if (d->has(CBM_AUTOGRAD)) d->requires_grad[h.id] = false;  // `insert`, not `entry().or_insert` (autograd.rs:86-91)
 }
 
 // Lazy::alloc_later (lazy.rs:175-181 + the callback at :345-380)
@@ -276,12 +289,14 @@ int32_t call_op(cbm_device *d, const Op &op)
 // AddOperation::add_op: Lazy records (lazy.rs:93-107), everything else runs now (base.rs:53-62)
 int32_t add_op(cbm_device *d, Op op)
 {
-    // "each parent (id) must be unique" (lazy_graph.rs:112-128)
-    for (size_t i = 0; i < op.arg_ids.size(); i++)
-        for (size_t j = i + 1; j < op.arg_ids.size(); j++)
-            if (op.arg_ids[i] == op.arg_ids[j])
-                return fail(CB_ERR_INVALID_ARG, "each parent (id) must be unique");
     if (d->recording()) {
+        // "each parent (id) must be unique": a check of Lazy's convert_to_operation only (lazy_graph.rs:112-128);
+        // Base::add_op just calls the operation (base.rs:53-62) and the kernels allow out == in — after
+        // optimize_mem_graph on Graph<Cached<..>> the buffers of a trace DO share one address
+        for (size_t i = 0; i < op.arg_ids.size(); i++)
+            for (size_t j = i + 1; j < op.arg_ids.size(); j++)
+                if (op.arg_ids[i] == op.arg_ids[j])
+                    return fail(CB_ERR_INVALID_ARG, "each parent (id) must be unique");
         d->ops.push_back(std::move(op));
         d->invalidate_replay();
         return CB_OK;
@@ -390,6 +405,66 @@ void free_replay(cbm_device *d)
     d->replay_valid = false;
 }
 
+
+// What a pass that destroys the intermediates x_1 .. x_{K-1} of a unary chain ids = [x_0, x_1, .., x_K] (unary
+// fusing: never written; memory-graph aliasing: overwritten) has to know about the Autograd tape.
+enum class TapePlan { NoTape, Fused, Blocked };
+
+// NoTape : no grad function touches an intermediate — nothing to do.
+// Fused  : the chain's K grad functions (buf = x_{k-1}, out = x_k) sit on the tape next to each other and nothing else
+//          touches an intermediate: they are replaced by ONE chain-grad entry (buf = x_0, out = x_K) that recomputes
+//          the intermediates from x_0 (CB_KERNEL_CHAIN_GRAD).
+// Blocked: the tape needs an intermediate in a way one kernel cannot replace — the caller must leave the chain alone.
+int32_t tape_plan_for_chain(cbm_device *d, const std::vector<uint64_t> &ids, TapePlan *plan)
+{
+    *plan = TapePlan::NoTape;
+    if (!d->has(CBM_AUTOGRAD) || d->tape.empty() || ids.size() < 3) return CB_OK;
+    const size_t K = ids.size() - 1;
+    auto is_intermediate = [&](uint64_t id) { return std::find(ids.begin() + 1, ids.end() - 1, id) != ids.end() - 1; };
+    std::vector<size_t> touching;
+    for (size_t p = 0; p < d->tape.size(); p++)
+        if (is_intermediate(d->tape[p].buf_id) || is_intermediate(d->tape[p].out_id)) touching.push_back(p);
+    if (touching.empty()) return CB_OK;
+    *plan = TapePlan::Blocked;
+    // the K entries must be tape[p0 .. p0+K), in chain order; the first of them is (x_0 -> x_1), which touches x_1
+    const size_t p0 = touching.front();
+    if (p0 + K > d->tape.size() || touching.size() != K || touching.back() != p0 + K - 1) return CB_OK;
+    const int32_t dtype = d->tape[p0].dtype;
+    for (size_t k = 0; k < K; k++) {
+        const GradOp &g = d->tape[p0 + k];
+        if (g.chain || g.buf_id != ids[k] || g.out_id != ids[k + 1] || g.dtype != dtype || g.fwd_ir.empty() || g.grad_ir.empty())
+            return CB_OK;
+    }
+    // one flag for the whole chain: backward() tests requires_grad of x_0 only
+    auto flag = [&](uint64_t id) {
+        auto it = d->requires_grad.find(id);
+        return it != d->requires_grad.end() && it->second;
+    };
+    for (size_t k = 1; k < K; k++)
+        if (flag(ids[k]) != flag(ids[0])) return CB_OK;
+    std::vector<const cb_node *> progs;
+    std::vector<int32_t> counts;
+    for (size_t k = 0; k < K; k++) {
+        progs.push_back(d->tape[p0 + k].fwd_ir.data());
+        counts.push_back((int32_t)d->tape[p0 + k].fwd_ir.size());
+    }
+    for (size_t k = 0; k < K; k++) {
+        progs.push_back(d->tape[p0 + k].grad_ir.data());
+        counts.push_back((int32_t)d->tape[p0 + k].grad_ir.size());
+    }
+    GradOp fused;
+    fused.buf_id = ids[0];
+    fused.out_id = ids[K];
+    fused.dtype = dtype;
+    fused.chain = true;
+    fused.chain_len = K;
+    CB_TRY(cb_expr_compile(d->raw, dtype, CB_KERNEL_CHAIN_GRAD, progs.data(), counts.data(), (int32_t)progs.size(), &fused.grad_expr));
+    d->tape.erase(d->tape.begin() + (ptrdiff_t)p0 + 1, d->tape.begin() + (ptrdiff_t)(p0 + K));
+    d->tape[p0] = std::move(fused);
+    *plan = TapePlan::Fused;
+    return CB_OK;
+}
+
 }  // namespace
 
 // ===================================================================== device
@@ -485,6 +560,29 @@ extern "C" int32_t cbm_buffer_drop(cbm_device *d, cbm_buf b)
     const bool last_ref = --d->id_refs[h->id] <= 0;
     if (last_ref) d->id_refs.erase(h->id);
     if (!is_grad_view && last_ref) d->buffers.erase(h->id);
+    if (h->owned && h->ptr && last_ref && d->has(CBM_AUTOGRAD)) {
+        // The id of an eager buffer is its address, and the pool hands a freed address straight back: state keyed by
+        // the id must not outlive the buffer, or the next buffer at that address inherits requires_grad and the old
+        // accumulated gradient.  (The reference never removes it — ids there are addresses too, autograd.rs:86-91.)
+        const uint64_t id = h->id;
+        d->requires_grad.erase(id);
+        auto gh = d->grad_handle.find(id);
+        if (gh != d->grad_handle.end()) {
+            Handle *view = d->handle(gh->second);
+            if (view) {
+                if (--d->id_refs[view->id] <= 0) d->id_refs.erase(view->id);
+                d->buffers.erase(view->id);
+                d->handles.erase(gh->second);  // the lent view dies with the gradient it points to
+            }
+            d->grad_handle.erase(gh);
+        }
+        auto g = d->grads.find(id);
+        if (g != d->grads.end()) {
+            d->buffers.erase(g->second.ptr);
+            cb_free(d->raw, g->second.ptr);
+            d->grads.erase(g);
+        }
+    }
     if (h->owned && h->ptr) CB_TRY(cb_free(d->raw, h->ptr));
     d->handles.erase(b);
     d->invalidate_replay();
@@ -662,7 +760,9 @@ extern "C" int32_t cbm_unary_ew(cbm_device *d, cbm_buf in, const cb_node *fwd, i
     g.out_id = d->handle(*out)->id;
     g.dtype = dtype;
     CB_TRY(compile_one(d, dtype, CB_KERNEL_UNARY_GRAD, grad, n_grad, &g.grad_expr));
-    d->tape.push_back(g);
+    g.fwd_ir.assign(fwd, fwd + n_fwd);
+    g.grad_ir.assign(grad, grad + n_grad);
+    d->tape.push_back(std::move(g));
     return CB_OK;
 }
 
@@ -677,7 +777,7 @@ extern "C" int32_t cbm_binary(cbm_device *d, int32_t op, cbm_buf lhs, cbm_buf rh
     const uint64_t lid = hl->id, rid = hr->id;
     const int32_t dtype = hl->dtype;
     const size_t len = hl->len;
-    if (lid == rid) return fail(CB_ERR_INVALID_ARG, "each parent (id) must be unique");  // lazy_graph.rs:112-128
+    if (lid == rid && d->recording()) return fail(CB_ERR_INVALID_ARG, "each parent (id) must be unique");  // lazy_graph.rs:112-128
     // README.md:96-122: retrieve(len, (lhs, rhs)) then add_op((lhs, rhs, &mut out), ..)
     const cbm_buf parents[2] = {lhs, rhs};
     cbm_buf ob = 0;
@@ -923,6 +1023,26 @@ extern "C" int32_t cbm_optimize_mem_graph(cbm_device *d)
             auto def = by_id.find(head->second);
             if (def == by_id.end()) continue;  // allocated earlier: nothing to share any more
             const Deferred a = def->second;
+            if (d->has(CBM_AUTOGRAD) && !d->tape.empty()) {
+                // sharing one allocation overwrites every buffer of the trace but the last; grad functions that read
+                // them must become one recomputing chain-grad kernel first, else the trace keeps its own buffers
+                std::vector<uint64_t> chain_ids;
+                auto prod = d->op_of_id.find(head->second);
+                if (prod != d->op_of_id.end() && prod->second < d->ops.size() && d->ops[prod->second].kind == OpKind::Apply &&
+                    d->ops[prod->second].arg_ids.size() == 2)
+                    chain_ids.push_back(d->ops[prod->second].arg_ids[1]);
+                else
+                    chain_ids.push_back(UINT64_MAX);  // no unary producer: an id no grad function can name
+                chain_ids.push_back(head->second);
+                for (size_t use : t.use_cache_idxs) {
+                    auto uid = d->idx_to_buf_id.find(use);
+                    if (uid != d->idx_to_buf_id.end()) chain_ids.push_back(uid->second);
+                }
+                // the head is overwritten too, so it counts as an intermediate: prepend the chain's real input
+                TapePlan plan = TapePlan::NoTape;
+                CB_TRY(tape_plan_for_chain(d, chain_ids, &plan));
+                if (plan == TapePlan::Blocked) continue;
+            }
             if (!d->allocated_ids.count(a.id)) {
                 if (d->buffers.count(a.id)) return fail(CB_ERR_STATE, "IDs collided! Maybe pointing address already occupied this ID.");
                 uint64_t p = 0;
@@ -952,6 +1072,20 @@ extern "C" int32_t cbm_optimize_mem_graph(cbm_device *d)
     // Cached::optimize_mem_graph (cached.rs:414-448): later iterations of the loop hand out the
     // head's allocation for every cursor position of the trace
     for (const CacheTrace &t : traces) {
+        if (d->has(CBM_AUTOGRAD)) {
+            // eager stacks re-record the tape every iteration; a trace whose buffers carry gradients keeps its own
+            // allocations (their values are what the next backward() reads)
+            bool needs_values = false;
+            std::vector<size_t> members{t.cache_idx};
+            members.insert(members.end(), t.use_cache_idxs.begin(), t.use_cache_idxs.end());
+            for (size_t m : members) {
+                auto id = d->idx_to_buf_id.find(m);
+                if (id == d->idx_to_buf_id.end()) continue;
+                auto rg = d->requires_grad.find(id->second);
+                needs_values = needs_values || (rg != d->requires_grad.end() && rg->second);
+            }
+            if (needs_values) continue;
+        }
         auto hc = d->idx_to_cursor.find(t.cache_idx);
         if (hc == d->idx_to_cursor.end()) return fail(CB_ERR_GRAPH_OPTIMIZATION, "GraphOptimization: trace head has no cursor");
         auto head = d->cache.find(hc->second);
@@ -1005,7 +1139,15 @@ extern "C" int32_t cbm_unary_fusing(cbm_device *d)
             const int32_t dtype = d->ops[(size_t)op_idx[i]].dtype;
             size_t j = i + 1;
             while (j < op_idx.size() && fusable(j, dtype, j - 1)) j++;
+            TapePlan plan = TapePlan::NoTape;
             if (j - i >= 2) {
+                // the grad functions of unary_ew read the buffers this run would stop writing: fuse them as well
+                // (one recomputing chain-grad kernel), or leave the run alone when that is not possible
+                std::vector<uint64_t> chain_ids{d->ops[(size_t)op_idx[i]].arg_ids[1]};
+                for (size_t k = i; k < j; k++) chain_ids.push_back(d->ops[(size_t)op_idx[k]].arg_ids[0]);
+                CB_TRY(tape_plan_for_chain(d, chain_ids, &plan));
+            }
+            if (j - i >= 2 && plan != TapePlan::Blocked) {
                 Op &first = d->ops[(size_t)op_idx[i]];
                 const Op &last = d->ops[(size_t)op_idx[j - 1]];
                 // out = the last op's output, in = the first op's input; they must differ (fusing.rs:60-67)
@@ -1188,10 +1330,22 @@ static int32_t backward_impl(cbm_device *d, cbm_buf out, const void *seed, size_
     GET_HANDLE(ho, d, out);
     Entry *og = nullptr;
     CB_TRY(grad_entry(d, ho->id, ho->len, ho->dtype, &og));
+    // The seed of ones can be folded into the first grad kernel of the replay (CB_GRAD_SEED_ONES: the kernel computes
+    // with 1 and WRITES out.grad instead of reading it) when that kernel is the one consuming out.grad and it will
+    // really run; otherwise out.grad is filled by its own pass, like `vec![T::one(); len]` + write in the reference.
+    bool seed_in_kernel = false;
+    if (!seed && !d->tape.empty()) {
+        const GradOp &last = d->tape.back();
+        const Entry *buf = d->resolve(last.buf_id);
+        const Entry *o = d->resolve(last.out_id);
+        auto rg = d->requires_grad.find(last.buf_id);
+        seed_in_kernel = last.out_id == ho->id && last.buf_id != ho->id && buf && o && buf->len == og->len &&
+                         rg != d->requires_grad.end() && rg->second;
+    }
     if (seed) {
         if (seed_len != og->len) return fail(CB_ERR_SHAPE, "seed of %zu elements for a buffer of %zu", seed_len, og->len);
         CB_TRY(cb_h2d(d->raw, og->ptr, seed, seed_len * dtype_size(og->dtype)));  // tape.rs:53-64
-    } else {
+    } else if (!seed_in_kernel) {
         CB_TRY(cb_fill(d->raw, og->dtype, og->ptr, og->len, 1.0, 1));  // vec![T::one(); len], on the device
     }
     // device.eagerly(|| tape.backward(..)): grad ops run now even under Lazy (tape.rs:78-82)
@@ -1212,7 +1366,9 @@ static int32_t backward_impl(cbm_device *d, cbm_buf out, const void *seed, size_
         Entry *bg = nullptr, *outg = nullptr;
         rc = grad_entry(d, g.buf_id, buf->len, buf->dtype, &bg);
         if (rc == CB_OK) rc = grad_entry(d, g.out_id, o->len, o->dtype, &outg);
-        if (rc == CB_OK) rc = cb_unary_grad(d->raw, g.grad_expr, buf->ptr, bg->ptr, outg->ptr, buf->len);
+        // one kernel per grad function; a chain entry stands for the K grad functions of a fused chain
+        const uint32_t flags = (seed_in_kernel && it == d->tape.rbegin()) ? CB_GRAD_SEED_ONES : 0u;
+        if (rc == CB_OK) rc = cb_unary_grad_ex(d->raw, g.grad_expr, buf->ptr, bg->ptr, outg->ptr, buf->len, flags);
     }
     d->lazy_enabled = lazy_was_enabled;
     if (!is_lazy_enabled) d->tape.clear();  // tape.rs:48-50

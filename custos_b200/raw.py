@@ -183,6 +183,11 @@ class RawDevice:
     def unary_grad(self, e: Expr, lhs: int, lhs_grad: int, out_grad: int, n: int):
         N.call("cb_unary_grad", self.h, e.handle, lhs, lhs_grad, out_grad, n)
 
+    def unary_grad_ex(self, e: Expr, lhs: int, lhs_grad: int, out_grad: int, n: int, flags: int = 0):
+        """add_unary_grad or the backward of a whole fused chain (an Expr of kind KERNEL_CHAIN_GRAD compiled from
+        the K forward closures followed by their K grad closures); flags: N.GRAD_SEED_ONES."""
+        N.call("cb_unary_grad_ex", self.h, e.handle, lhs, lhs_grad, out_grad, n, flags)
+
     def apply_host(self, e: Expr, host_in: int, host_out: int, n: int):
         """out_host[i] = f(in_host[i]) with H2D / kernel / D2H overlapped chunk by chunk (raw host addresses)."""
         N.call("cb_apply_host", self.h, e.handle, C.c_void_p(host_in), C.c_void_p(host_out), n)

@@ -145,7 +145,13 @@ int32_t cb_ops_to_fused_src(int32_t dtype, const cb_node *const *progs, const in
 typedef enum cb_kernel_kind {
     CB_KERNEL_APPLY = 0,       /* out[i] = fN(...f1(in[i]))              K1/K2, a1/a8 */
     CB_KERNEL_UNARY_GRAD = 1,  /* lhs_grad[i] += out_grad[i] * g(lhs[i]) K3, a2       */
-    CB_KERNEL_BINARY = 2       /* out[i] = f(lhs[i], rhs[i])             a5 (+ f2)    */
+    CB_KERNEL_BINARY = 2,      /* out[i] = f(lhs[i], rhs[i])             a5 (+ f2)    */
+    CB_KERNEL_CHAIN_GRAD = 3   /* the backward of a fused chain of K unary_ew ops in ONE kernel:
+                                  x_grad[i] += (((out_grad[i] * gK(x_{K-1})) ...) * g1(x_0)), x_k = f_k(x_{k-1})
+                                  recomputed from x_0 = x[i] in registers.  Programs: f_1..f_K, then g_1..g_K
+                                  (n_progs = 2K).  Same roundings, in the same order, as the K add_unary_grad
+                                  calls the tape would replay (src/unary.rs:118-128,
+                                  src/modules/autograd/tape.rs:39-47) with zeroed intermediate gradients */
 } cb_kernel_kind;
 
 int32_t cb_expr_cuda_source(int32_t dtype, int32_t kind, const cb_node *const *progs,
@@ -224,6 +230,13 @@ int32_t cb_apply(cb_device *dev, cb_expr *f, uint64_t in, uint64_t out, size_t n
  * (src/devices/cpu_stack_ops.rs:28). */
 int32_t cb_unary_grad(cb_device *dev, cb_expr *g, uint64_t lhs, uint64_t lhs_grad,
                       uint64_t out_grad, size_t n);
+/* The same for expressions of kind CB_KERNEL_UNARY_GRAD or CB_KERNEL_CHAIN_GRAD, with flags:
+ * CB_GRAD_SEED_ONES — out_grad is not read but WRITTEN with T::one() and the kernel computes with 1: the seed of
+ * `backward()` (`vec![T::one(); len]`, src/buffer/impl_autograd.rs:32) folded into the first grad kernel of the
+ * replay instead of a separate fill pass over the buffer. */
+#define CB_GRAD_SEED_ONES 1u
+int32_t cb_unary_grad_ex(cb_device *dev, cb_expr *g, uint64_t lhs, uint64_t lhs_grad,
+                         uint64_t out_grad, size_t n, uint32_t flags);
 /* two-marker expression: out[i] = f(lhs[i], rhs[i]) */
 int32_t cb_apply2(cb_device *dev, cb_expr *f, uint64_t lhs, uint64_t rhs, uint64_t out, size_t n);
 

@@ -189,9 +189,12 @@ DEFINE_FLOAT_EVAL(eval_f64, double, exp, log, sin, cos, tan, tanh, pow, fabs)
  * Float for half::f16 (src/number.rs:543-608) and half::bf16 (:611-676): every function goes
  * to f32 and back (`Self::from_f32(self.to_f32().exp())`), `tan` calls cos (lines 575-577 and
  * 643-645); + - * / are `half`'s operators (f32 arithmetic, rounded back after each op).
- * Number::max for f16 forwards to half's inherent f16::max (number.rs:537-539), which keeps
- * `self` unless `other > self`; bf16 (number.rs:515-531) and both mins use the trait defaults
- * `if self > rhs { self } else { rhs }` / `if self < rhs { self } else { rhs }` (:202-209). */
+ * Number::max for f16 (number.rs:507-510) AND for bf16 (number.rs:536-539) forwards to half's
+ * inherent `max`, which keeps `self` unless `other > self` (half 2.x: `if other > self &&
+ * !other.is_nan() { other } else { self }` — so a NaN `self` stays, a NaN `other` is ignored,
+ * and +0 / -0 ties keep `self`); both mins use the trait default
+ * `if self < rhs { self } else { rhs }` (:207-209).  (Round 1 gave bf16 the trait default
+ * `if self > rhs { self } else { rhs }` for max: a misreading of number.rs:515-540.) */
 static uint16_t eval_half(int bf, const orc_node *nd, int n, uint16_t x, uint16_t y)
 {
 #define TO_F32(h) (bf ? orc_bf16_to_f32(h) : orc_f16_to_f32(h))
@@ -213,7 +216,7 @@ static uint16_t eval_half(int bf, const orc_node *nd, int n, uint16_t x, uint16_
         case ORC_OP_DIV: r = FROM_F32(a / b); break;
         case ORC_OP_POW: r = FROM_F32(powf(a, b)); break;
         case ORC_OP_MIN: r = (a < b) ? ha : hb; break;
-        case ORC_OP_MAX: r = bf ? ((a > b) ? ha : hb) : ((b > a) ? hb : ha); break;
+        case ORC_OP_MAX: r = (b > a) ? hb : ha; break;
         case ORC_OP_SIN: r = FROM_F32(sinf(a)); break;
         case ORC_OP_COS: r = FROM_F32(cosf(a)); break;
         case ORC_OP_TAN: r = FROM_F32(cosf(a)); break; /* sic */

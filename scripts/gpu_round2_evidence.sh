@@ -22,3 +22,5 @@ LD_PRELOAD="$ASAN:$UBSAN" ASAN_OPTIONS=detect_leaks=0:protect_shadow_gap=0:halt_
   CUSTOS_B200_LIB=custos_b200/lib/libcustos_b200_asan.so \
   python -m pytest tests/test_gpu_modules.py tests/test_gpu_fuzz_modules.py tests/test_gpu_reference_suite.py tests/test_gpu_untyped.py -m gpu -q -p no:cacheprovider > gpurun_out/asan_gpu.log 2>&1
 tail -3 gpurun_out/asan_gpu.log
+# host topology of the box (for the multi-GPU end-to-end analysis)
+{ nvidia-smi topo -m; echo; numactl -H 2>/dev/null || echo "no numactl"; echo; lscpu | head -30; echo; cat /sys/bus/pci/devices/*/numa_node 2>/dev/null | sort | uniq -c; nproc; free -g; } > gpurun_out/r2_topology_n1.txt 2>&1

@@ -90,5 +90,33 @@ def dtype_vectors():
     return out
 
 
+def half_minmax_kats():
+    """Known answers for Number::min / Number::max on f16 and bf16 over {+-0, +-1, +-inf, NaN} x both operand
+    orders, derived here from the reference text alone (NOT from the oracle):
+      max: `self.max(rhs)` -> half's inherent max (src/number.rs:507-510 for f16, :536-539 for bf16):
+           `if other > self && !other.is_nan() { other } else { self }`
+      min: the Number default (src/number.rs:207-209): `if self < rhs { self } else { rhs }`
+    Comparisons are IEEE (NaN compares false, +0 == -0)."""
+    import json
+    import math
+    vals = {"f16": {"+0": 0x0000, "-0": 0x8000, "1": 0x3c00, "-1": 0xbc00, "inf": 0x7c00, "-inf": 0xfc00, "nan": 0x7e00},
+            "bf16": {"+0": 0x0000, "-0": 0x8000, "1": 0x3f80, "-1": 0xbf80, "inf": 0x7f80, "-inf": 0xff80, "nan": 0x7fc0}}
+    num = {"+0": 0.0, "-0": -0.0, "1": 1.0, "-1": -1.0, "inf": math.inf, "-inf": -math.inf, "nan": math.nan}
+    out = {}
+    for ty, bits in vals.items():
+        rows = []
+        for a in bits:
+            for b in bits:
+                mx = b if (num[b] > num[a] and not math.isnan(num[b])) else a
+                mn = a if num[a] < num[b] else b
+                rows.append({"self": a, "rhs": b, "self_bits": bits[a], "rhs_bits": bits[b],
+                             "max_bits": bits[mx], "min_bits": bits[mn]})
+        out[ty] = rows
+    path = Path(__file__).resolve().parent / "half_minmax_kats.json"
+    path.write_text(json.dumps(out, indent=1) + "\n")
+    print("wrote", path.name, sum(len(v) for v in out.values()), "cases")
+
+
 if __name__ == "__main__":
     main()
+    half_minmax_kats()

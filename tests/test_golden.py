@@ -256,3 +256,43 @@ def test_gpu_against_the_dtype_vectors(raw_device):
         p = dev.upload(x)
         assert dev.sum(dt, p, x.size) == g[f"sum_{name}"][0]
         dev.free(p)
+
+
+# ------------------------------------------------------------------ f16 / bf16 min / max over {+-0, +-1, +-inf, NaN}
+def _minmax_cases():
+    import json
+    kats = json.loads((GOLDEN / "half_minmax_kats.json").read_text())
+    for ty, dt in (("f16", orc.F16), ("bf16", orc.BF16)):
+        a = np.array([r["self_bits"] for r in kats[ty]], np.uint16)
+        b = np.array([r["rhs_bits"] for r in kats[ty]], np.uint16)
+        mx = np.array([r["max_bits"] for r in kats[ty]], np.uint16)
+        mn = np.array([r["min_bits"] for r in kats[ty]], np.uint16)
+        yield ty, dt, a, b, mx, mn
+
+
+def _as_dtype(bits, dt):
+    return bits.view(np.float16) if dt == orc.F16 else bits
+
+
+def test_oracle_half_min_max_known_answers():
+    """src/number.rs:507-510 and :536-539 (max -> half's inherent max) and :207-209 (min): 49 operand pairs each;
+    the expected bits come from the reference text (tests/golden/make_golden.py: half_minmax_kats), not the oracle."""
+    for ty, dt, a, b, mx, mn in _minmax_cases():
+        got_max = orc.apply2(lambda p, q: p.max(q), dt, _as_dtype(a, dt), _as_dtype(b, dt)).view(np.uint16)
+        got_min = orc.apply2(lambda p, q: p.min(q), dt, _as_dtype(a, dt), _as_dtype(b, dt)).view(np.uint16)
+        assert got_max.tolist() == mx.tolist(), ty
+        assert got_min.tolist() == mn.tolist(), ty
+
+
+@pytest.mark.gpu
+def test_gpu_half_min_max_known_answers(raw_device):
+    dev = raw_device
+    for ty, dt, a, b, mx, mn in _minmax_cases():
+        ndt = N.F16 if dt == orc.F16 else N.BF16
+        pa, pb, po = dev.upload(_as_dtype(a, dt)), dev.upload(_as_dtype(b, dt)), dev.alloc(a.nbytes)
+        for f, want in ((lambda p, q: p.max(q), mx), (lambda p, q: p.min(q), mn)):
+            dev.apply2(dev.compile(f, ndt, N.KERNEL_BINARY), pa, pb, po, a.size)
+            got = np.asarray(dev.d2h(po, a.size, ndt)).view(np.uint16)
+            assert got.tolist() == want.tolist(), ty
+        for p in (pa, pb, po):
+            dev.free(p)

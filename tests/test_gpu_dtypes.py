@@ -112,8 +112,8 @@ def test_transcendental_bf16_every_value(raw_device, name):
 
 
 def test_f16_max_keeps_self_on_ties(raw_device):
-    # src/number.rs:537-539: Number::max for f16 is half's inherent max (`other > self ? other : self`); every other
-    # float takes the trait default (`self > rhs ? self : rhs`).  They differ on +0 / -0.
+    # src/number.rs:507-510 and :536-539: Number::max for f16 AND bf16 is half's inherent max (`other > self ? other :
+    # self`); f32 / f64 take the trait default (`self > rhs ? self : rhs`).  They differ on +0 / -0.
     dev = raw_device
     a, b = np.array([0.0, -0.0, 1.0, 2.0], np.float16), np.array([-0.0, 0.0, 2.0, 1.0], np.float16)
     for dt, (x, y) in ((N.F16, (a, b)), (N.F32, (a.astype(np.float32), b.astype(np.float32))),

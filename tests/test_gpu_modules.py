@@ -643,3 +643,172 @@ def test_elementwise_fusing_keeps_buffers_a_grad_function_needs():
         assert_ulp(h.replace().read(), np.sin(np.array([1., 2., 3., 4.], np.float32)), 2)
         out.backward()
         assert_ulp(buf.grad().read(), (2.0 * np.cos(np.array([1., 2., 3., 4.]))).astype(np.float32), 4)
+
+
+# ------------------------------------------------------------------ fused forward + fused backward (north-star stack)
+def _unfused_chain8(x, seed=None):
+    """The reference behaviour on the device: 8 kernels forward, 8 add_unary_grad kernels backward."""
+    with CUDA("Lazy", "Graph", "Autograd", "Base") as dev:
+        buf = dev.buffer(x).require_grad()
+        cur = buf
+        for f, g in zip(CHAIN8, CHAIN8_GRADS):
+            cur = dev.unary_ew(cur, f, g)
+        dev.run()
+        if seed is None:
+            cur.backward()
+        else:
+            cur.backward_with(seed)
+        return cur.replace().read(), buf.grad().read()
+
+
+@pytest.mark.parametrize("order", ["fuse", "alias_then_fuse", "fuse_then_alias"])
+def test_fused_chain8_forward_and_backward_are_two_kernels(order):
+    # BASELINE configs[2] on CUDA<Lazy<Graph<Autograd<Base>>>>: unary_fusing on a stack whose tape reads the
+    # intermediates (src/unary.rs:118-128 vs src/modules/lazy/optimization.rs:77-91).  One forward kernel, one
+    # recomputing backward kernel, gradients bit-identical to the 8 + 8 kernel path.
+    n = 100_003
+    x = random_inputs(N.F32, n, 4, -4, 4)
+    x[:12] = [0.0, -0.0, np.inf, -np.inf, np.nan, 3e5, -2.5e6, 1e-40, -1e-40, 88.0, -104.0, 1e30]  # redo path, edges
+    want_out, want_grad = _unfused_chain8(x)
+    with CUDA("Lazy", "Graph", "Autograd", "Base") as dev:
+        buf = dev.buffer(x).require_grad()
+        cur = buf
+        for f, g in zip(CHAIN8, CHAIN8_GRADS):
+            cur = dev.unary_ew(cur, f, g)
+        if order == "alias_then_fuse":
+            dev.optimize_mem_graph()
+        dev.unary_fusing()
+        if order == "fuse_then_alias":
+            dev.optimize_mem_graph()
+        before = dev.raw.launches
+        dev.run()
+        assert dev.raw.launches - before <= 2  # the fused chain (+ the zero-fill of its deferred output allocation)
+        assert_bit_exact(cur.replace().read(), want_out, "fused forward == unfused forward")
+        cur.backward()
+        got = buf.grad().read()
+        assert_bit_exact(got, want_grad, "one chain-grad kernel == eight add_unary_grad kernels")
+        assert np.all(cur.grad().read() == 1.0)  # the seed is written by the grad kernel itself
+        # steady state: forward = 1 launch, backward = 1 launch (seed folded in, gradient buffers exist)
+        before = dev.raw.launches
+        dev.run()
+        assert dev.raw.launches - before == 1
+        before = dev.raw.launches
+        cur.backward()
+        assert dev.raw.launches - before == 1
+        twice = buf.grad().read()
+        with np.errstate(all="ignore"):
+            assert_bit_exact(twice, (got + got).astype(np.float32), "second backward accumulates into x.grad")
+
+
+def test_fused_backward_with_an_explicit_seed_and_zero_grad():
+    n = 4099
+    x = random_inputs(N.F32, n, 14, -4, 4)
+    seed = random_inputs(N.F32, n, 15, -2, 2)
+    seed[:4] = [0.0, -0.0, 1.0, -1.0]
+    _, want_grad = _unfused_chain8(x, seed)
+    with CUDA("Lazy", "Graph", "Autograd", "Base") as dev:
+        buf = dev.buffer(x).require_grad()
+        cur = buf
+        for f, g in zip(CHAIN8, CHAIN8_GRADS):
+            cur = dev.unary_ew(cur, f, g)
+        dev.unary_fusing()
+        dev.run()
+        cur.backward_with(seed)
+        assert_bit_exact(buf.grad().read(), want_grad, "seeded chain-grad")
+        dev.zero_grad()
+        assert np.all(buf.grad().read() == 0)
+        cur.backward_with(seed)
+        assert_bit_exact(buf.grad().read(), want_grad, "after zero_grad")
+
+
+def test_unary_fusing_leaves_a_chain_alone_when_only_part_of_it_is_on_the_tape():
+    # apply_fn records no grad function: the tape reads x1 (input of the unary_ew op) — fusing it away would feed
+    # zeros to add_unary_grad.  The run stays unfused and the gradient stays right.
+    n = 1000
+    x = random_inputs(N.F32, n, 16, -2, 2)
+    with CUDA("Lazy", "Graph", "Autograd", "Base") as dev:
+        buf = dev.buffer(x).require_grad()
+        x1 = dev.apply_fn(buf, lambda v: v.mul(2.0))
+        x2 = dev.unary_ew(x1, lambda v: v.sin(), lambda v: v.cos())
+        x3 = dev.apply_fn(x2, lambda v: v.add(1.0))
+        dev.unary_fusing()
+        dev.optimize_mem_graph()
+        dev.run()
+        a1 = orc.apply_fn(lambda v: v.mul(2.0), orc.F32, x)
+        assert_bit_exact(x1.replace().read(), a1, "x1 is still materialised")
+        x2.backward()
+        g = x1.grad().read()
+        dev_cos = orc.apply_fn(lambda v: v.cos(), orc.F32, a1)
+        assert_ulp(g, dev_cos, 4, "d sin(x1) / d x1")
+        assert float(np.max(np.abs(x3.replace().read() - (np.sin(a1.astype(np.float64)) + 1)))) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f16", "bf16", "i32"])
+def test_fused_backward_other_dtypes_match_the_unfused_device_result(dtype):
+    n = 10_007
+    if dtype == "i32":
+        code, fwd, grads = N.I32, [lambda v: v.add(3), lambda v: v.mul(5), lambda v: v.sub(7)], \
+            [lambda v: v.add(1), lambda v: v.mul(2), lambda v: 3]
+        x = np.random.default_rng(3).integers(-1000, 1000, n).astype(np.int32)
+    else:
+        code = {"f64": N.F64, "f16": N.F16, "bf16": N.BF16}[dtype]
+        fwd, grads = CHAIN8, CHAIN8_GRADS
+        x = random_inputs(code, n, 17, -4, 4)
+    results = []
+    for fuse in (False, True):
+        with CUDA("Lazy", "Graph", "Autograd", "Base", dtype=code) as dev:
+            buf = dev.buffer(x, dtype=code).require_grad()
+            cur = buf
+            for f, g in zip(fwd, grads):
+                cur = dev.unary_ew(cur, f, g)
+            if fuse:
+                dev.unary_fusing()
+            before = dev.raw.launches
+            dev.run()
+            assert (dev.raw.launches - before <= 2) == fuse
+            cur.backward()
+            results.append((cur.replace().read(), buf.grad().read()))
+    assert results[0][0].tobytes() == results[1][0].tobytes(), "forward"
+    assert results[0][1].tobytes() == results[1][1].tobytes(), "backward"
+
+
+def test_cached_graph_runs_in_place_after_optimize_mem_graph():
+    # Graph<Cached<Base>>: ids are device addresses; after optimize_mem_graph the buffers of a trace share one
+    # address, so the next iteration's apply_fn(a) -> b has out == in.  Base::add_op just runs it (base.rs:53-62).
+    x = random_inputs(N.F32, 5000, 18, -1, 1)
+    with CUDA("Graph", "Cached", "Base") as dev:
+        buf = dev.buffer(x)
+        want = orc.apply_chain([lambda v: v.mul(2.0), lambda v: v.add(1.0), lambda v: v.neg()], orc.F32, x)
+        for it in dev.range(4):
+            a = dev.apply_fn(buf, lambda v: v.mul(2.0))
+            b = dev.apply_fn(a, lambda v: v.add(1.0))
+            c = dev.apply_fn(b, lambda v: v.neg())
+            assert_bit_exact(c.read(), want, f"iteration {it}")
+            if it == 0:
+                dev.optimize_mem_graph()
+            else:
+                assert a.ptr() == b.ptr() == c.ptr()
+    with CUDA("Base") as dev:  # eager x op x is legal too
+        v = dev.buffer(x)
+        assert_bit_exact(dev.add(v, v).read(), orc.binary(0, orc.F32, x, x), "x + x")
+
+
+def test_autograd_state_does_not_survive_the_buffer():
+    # ids of eager buffers are device addresses and the pool recycles them: a new buffer at the address of a dropped
+    # one must not inherit requires_grad or the accumulated gradient
+    with CUDA("Autograd", "Base") as dev:
+        seen = False
+        for _ in range(8):
+            a = dev.buffer([1., 2., 3., 4.]).require_grad()
+            out = dev.unary_ew(a, lambda v: v.mul(2.0), lambda v: 2.0)
+            out.backward()
+            assert a.grad().read().tolist() == [2.] * 4
+            addr = a.ptr()
+            out.drop()
+            a.drop()
+            b = dev.buffer([5., 6., 7., 8.])
+            seen = seen or b.ptr() == addr
+            assert not b.requires_grad()
+            assert b.grad().read().tolist() == [0.] * 4
+            b.drop()
+        assert seen, "the pool never recycled an address: the test did not exercise the case"

@@ -84,8 +84,8 @@ def interpret_word_function(body: str, h: Half, x: np.ndarray, y=None) -> np.nda
                 env[name] = arith(np.abs, a)
             elif op == "min":
                 env[name] = select(lambda p, q: p < q, a, b, a, b)
-            elif op == "max":  # f16: half's inherent max keeps `self` unless other > self; bf16: the trait default
-                env[name] = select(lambda p, q: q > p, a, b, b, a) if h.dt == N.F16 else select(lambda p, q: p > q, a, b, a, b)
+            elif op == "max":  # f16 and bf16 (number.rs:507-510, 536-539): half's inherent max keeps `self` unless other > self
+                env[name] = select(lambda p, q: q > p, a, b, b, a)
             elif op in ("geq", "leq", "eq"):
                 cmp = (lambda p, q: p >= q) if op == "geq" else (lambda p, q: p <= q)
                 env[name] = select(cmp, a, b, one, zero)

@@ -213,14 +213,15 @@ def test_f16_tan_is_cos_like_the_reference():
 
 
 def test_f16_max_is_halfs_inherent_max():
-    # src/number.rs:537-539: Number::max for f16 forwards to half's f16::max, which keeps `self` unless
-    # `other > self`; the trait default (f32, f64, bf16; number.rs:202-204) returns `rhs` unless `self > rhs`.
+    # src/number.rs:507-510 (f16) and :536-539 (bf16): Number::max forwards to half's inherent max, which keeps `self`
+    # unless `other > self`; the trait default (f32, f64; number.rs:202-204) returns `rhs` unless `self > rhs`.
     # The two only differ for equal values with different bits (+0 / -0) and for NaN operands.
     pz, nz = np.float16(0.0), np.float16(-0.0)
     assert orc.eval_scalar(lambda x, y: x.max(y), F16, pz, nz).view(np.uint16) == 0x0000
     assert orc.eval_scalar(lambda x, y: x.max(y), F16, nz, pz).view(np.uint16) == 0x8000
     assert orc.eval_scalar(lambda x, y: x.max(y), F32, 0.0, -0.0).view(np.uint32) == 0x80000000
-    assert orc.eval_scalar(lambda x, y: x.max(y), orc.BF16, 0x0000, 0x8000) == 0x8000
+    assert orc.eval_scalar(lambda x, y: x.max(y), orc.BF16, 0x0000, 0x8000) == 0x0000
+    assert orc.eval_scalar(lambda x, y: x.max(y), orc.BF16, 0x8000, 0x0000) == 0x8000
     assert orc.eval_scalar(lambda x, y: x.min(y), F16, pz, nz).view(np.uint16) == 0x8000  # default min: rhs
 
 
