@@ -100,6 +100,11 @@ SIGNATURES = {
     "cb_comm_uses_peer_memory": [_vp, _P(_i32)],
     "cb_comm_sum": [_vp, _i32, _u64, _sz, _u64],
     "cb_comm_mean": [_vp, _i32, _u64, _sz, _sz, _u64],
+    "cb_comm_sum_host": [_vp, _i32, _u64, _sz, _vp],
+    "cb_comm_mean_host": [_vp, _i32, _u64, _sz, _sz, _vp],
+    "cb_comm_check": [_vp],
+    "cb_comm_rank": [_vp, _P(_i32), _P(_i32)],
+    "cb_comm_device": [_vp, _P(_vp)],
     "cb_shard_range": [_sz, _i32, _i32, _i32, _P(_sz), _P(_sz)],
     # module layer
     "cbm_device_create": [_i32, _u32, _i32, _P(_vp)],

@@ -73,7 +73,9 @@ struct cb_comm {
     cb::XchgSlot *xchg = nullptr;                 // this rank's buffer: 2 parities x n_ranks slots
     std::vector<void *> opened;                   // peers' buffers mapped through CUDA IPC
     cb::XchgSlot **peer_tbl = nullptr;            // device array of n_ranks buffer addresses
-    int *status = nullptr;                        // device flag: a peer timed out
+    int *status = nullptr;                        // host-mapped flag: call number of an exchange in which a peer timed out
+    int *status_dev = nullptr;                    // ... its device-side address
+    long long timeout_cycles = 4000000000ll;      // ~2 s of SM clock (CB_COMM_TIMEOUT_MS)
     unsigned long long epoch = 0;
 };
 
@@ -85,9 +87,13 @@ static bool setup_p2p(cb_comm *c)
         if (v[0] == '0') return false;
     if (c->n_ranks > cb::kMaxRanks) return false;
     const size_t bytes = sizeof(cb::XchgSlot) * 2 * (size_t)c->n_ranks;
+    // the timeout flag lives in mapped pinned host memory: the host can look at it without touching the stream
     bool ok = cudaMalloc(reinterpret_cast<void **>(&c->xchg), bytes) == cudaSuccess &&
-              cudaMemset(c->xchg, 0, bytes) == cudaSuccess && cudaMalloc(reinterpret_cast<void **>(&c->status), sizeof(int)) == cudaSuccess &&
-              cudaMemset(c->status, 0, sizeof(int)) == cudaSuccess;
+              cudaMemset(c->xchg, 0, bytes) == cudaSuccess &&
+              cudaHostAlloc(reinterpret_cast<void **>(&c->status), sizeof(int), cudaHostAllocMapped) == cudaSuccess &&
+              cudaHostGetDevicePointer(reinterpret_cast<void **>(&c->status_dev), c->status, 0) == cudaSuccess;
+    if (ok) *c->status = 0;
+    c->timeout_cycles = (long long)cb::env_int("CB_COMM_TIMEOUT_MS", 2000, 1, 600000) * 2000000ll;  // ~2 GHz
     cudaIpcMemHandle_t mine;
     std::memset(&mine, 0, sizeof mine);
     ok = ok && cudaIpcGetMemHandle(&mine, c->xchg) == cudaSuccess;
@@ -208,7 +214,7 @@ extern "C" int32_t cb_comm_destroy(cb_comm *c)
     cudaStreamSynchronize(c->dev->stream);
     for (void *p : c->opened) cudaIpcCloseMemHandle(p);
     if (c->peer_tbl) cudaFree(c->peer_tbl);
-    if (c->status) cudaFree(c->status);
+    if (c->status) cudaFreeHost(c->status);
     if (c->xchg) cudaFree(c->xchg);
     if (c->comm) nccl().CommDestroy(c->comm);
     if (c->local) cudaFree(c->local);
@@ -217,27 +223,48 @@ extern "C" int32_t cb_comm_destroy(cb_comm *c)
     return CB_OK;
 }
 
+// A peer that never arrived makes the exchange kernel give up (instead of hanging the GPU) and record the call number
+// in the host-mapped flag; the value the kernel then wrote is NOT the global sum.  Reported here, at every later
+// cb_comm_* call and by cb_comm_check, until the communicator is destroyed.
+static int32_t comm_status(cb_comm *c)
+{
+    if (c->p2p && c->status && *reinterpret_cast<volatile int *>(c->status) != 0)
+        return fail(CB_ERR_STATE, "cb_comm: a peer did not reach exchange %d within the timeout (CB_COMM_TIMEOUT_MS); "
+                                  "the result of that call is not the global sum", *reinterpret_cast<volatile int *>(c->status));
+    return CB_OK;
+}
+
+extern "C" int32_t cb_comm_check(cb_comm *c)
+{
+    CB_CHECK_ARG(c, "null communicator");
+    CB_TRY(c->dev->use());
+    cudaError_t e = cudaStreamSynchronize(c->dev->stream);
+    if (e != cudaSuccess) return c->dev->cuda_fail(e, "cudaStreamSynchronize");
+    return comm_status(c);
+}
+
 static int32_t comm_reduce(cb_comm *c, int32_t dtype, uint64_t in, size_t n_local, uint64_t out, size_t divisor)
 {
     CB_CHECK_ARG(c && cb::valid_dtype(dtype) && out, "bad argument");
+    CB_TRY(comm_status(c));
     if (dtype == CB_BOOL) return cb::fail(CB_ERR_UNSUPPORTED, "bool has no arithmetic in the reference (storage only)");
     cb_device *dev = c->dev;
     CB_TRY(dev->use());
     if (c->p2p) {
-        // pass 1 + ONE kernel that folds the partials, exchanges the totals over NVLink peer memory and
+        // ONE kernel reduces the slice, folds the partials, exchanges the totals over NVLink peer memory and
         // folds them in rank order
         cb::XchgArgs x;
         x.peers = c->peer_tbl;
         x.n_ranks = c->n_ranks;
         x.rank = c->rank;
         x.epoch = ++c->epoch;
-        x.timeout_cycles = 4000000000ll;  // ~2 s of SM clock
-        x.status = c->status;
+        x.timeout_cycles = c->timeout_cycles;
+        x.status = c->status_dev;
         if (n_local && !in) return fail(CB_ERR_INVALID_ARG, "null buffer");
         cudaError_t e = cb::launch_sum_exchange(dev->ctx(), dtype, reinterpret_cast<const void *>(in), n_local, dev->sum_partials,
-                                                reinterpret_cast<void *>(out), divisor, x);
-        if (e != cudaSuccess) return dev->cuda_fail(e, "sum exchange kernels");
-        dev->launches += n_local ? 2 : 1;
+                                                dev->sum_ticket, reinterpret_cast<void *>(out), divisor, x);
+        if (e != cudaSuccess) return dev->cuda_fail(e, "sum + exchange kernel");
+        dev->launches += 1;  // reduce, fold and exchange are one launch
         return CB_OK;
     }
     // a rank may own an empty slice (n smaller than the rank count): its partial is 0
@@ -265,4 +292,44 @@ extern "C" int32_t cb_comm_mean(cb_comm *c, int32_t dtype, uint64_t in, size_t n
 {
     if (!n_global) return fail(CB_ERR_ZERO_LENGTH, "mean over a zero length buffer");
     return comm_reduce(c, dtype, in, n_local, out, n_global);
+}
+
+static size_t comm_acc_bytes(int32_t dtype) { return (dtype == CB_F32 || cb::is_half_dtype(dtype)) ? 4 : 8; }
+
+static int32_t comm_reduce_host(cb_comm *c, int32_t dtype, uint64_t in, size_t n_local, void *host_out, size_t divisor)
+{
+    CB_CHECK_ARG(c && host_out, "null argument");
+    cb_device *dev = c->dev;
+    CB_TRY(comm_reduce(c, dtype, in, n_local, reinterpret_cast<uint64_t>(dev->sum_scalar), divisor));
+    cudaError_t e = cudaMemcpyAsync(dev->sum_host, dev->sum_scalar, comm_acc_bytes(dtype), cudaMemcpyDeviceToHost, dev->stream);
+    if (e != cudaSuccess) return dev->cuda_fail(e, "cudaMemcpyAsync");
+    CB_TRY(cb_comm_check(c));  // synchronises; a timed-out exchange is an error, not a number
+    std::memcpy(host_out, dev->sum_host, comm_acc_bytes(dtype));
+    return CB_OK;
+}
+
+extern "C" int32_t cb_comm_sum_host(cb_comm *c, int32_t dtype, uint64_t in, size_t n_local, void *host_out)
+{
+    return comm_reduce_host(c, dtype, in, n_local, host_out, 0);
+}
+
+extern "C" int32_t cb_comm_mean_host(cb_comm *c, int32_t dtype, uint64_t in, size_t n_local, size_t n_global, void *host_out)
+{
+    if (!n_global) return fail(CB_ERR_ZERO_LENGTH, "mean over a zero length buffer");
+    return comm_reduce_host(c, dtype, in, n_local, host_out, n_global);
+}
+
+extern "C" int32_t cb_comm_rank(cb_comm *c, int32_t *rank, int32_t *n_ranks)
+{
+    CB_CHECK_ARG(c, "null communicator");
+    if (rank) *rank = c->rank;
+    if (n_ranks) *n_ranks = c->n_ranks;
+    return CB_OK;
+}
+
+extern "C" int32_t cb_comm_device(cb_comm *c, cb_device **dev)
+{
+    CB_CHECK_ARG(c && dev, "null argument");
+    *dev = c->dev;
+    return CB_OK;
 }

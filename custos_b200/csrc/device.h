@@ -59,6 +59,7 @@ struct Tunables {
     std::string dump_dir;  // CB_DUMP_DIR: write generated sources and cubins here
 };
 const Tunables &tunables();
+int env_int(const char *name, int dflt, int lo, int hi);
 
 // Driver entry points, resolved through cudaGetDriverEntryPoint so the library carries no
 // link-time dependency on libcuda (it must load on a machine without a driver).
@@ -117,6 +118,7 @@ struct cb_device {
 
     // reduction scratch
     void *sum_partials = nullptr;  // kSumMaxBlocks x 8 bytes
+    unsigned int *sum_ticket = nullptr;  // device counter of the one-launch sum (last block folds); zero between launches
     void *sum_scalar = nullptr;    // 8 bytes device
     void *sum_host = nullptr;      // 8 bytes pinned
 

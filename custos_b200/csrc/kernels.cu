@@ -113,9 +113,12 @@ struct BinOp {  // integers: wrapping, x / 0 = 0
     typedef typename std::make_unsigned<T>::type U;
     static __device__ __forceinline__ T apply(T a, T b)
     {
-        if (OP == CB_BIN_ADD) return (T)((U)a + (U)b);
-        if (OP == CB_BIN_MUL) return (T)((U)a * (U)b);
-        if (OP == CB_BIN_SUB) return (T)((U)a - (U)b);
+        // (8- and 16-bit operands are widened to unsigned int explicitly: `U * U` would promote to SIGNED int and
+        // 65535 * 65535 overflows it)
+        typedef typename std::conditional<(sizeof(T) < 4), unsigned int, U>::type W;
+        if (OP == CB_BIN_ADD) return (T)(U)((W)(U)a + (W)(U)b);
+        if (OP == CB_BIN_MUL) return (T)(U)((W)(U)a * (W)(U)b);
+        if (OP == CB_BIN_SUB) return (T)(U)((W)(U)a - (W)(U)b);
         if (b == (T)0) return (T)0;
         if ((T)-1 < (T)0 && b == (T)-1) return (T)((U)0 - (U)a);  // MIN / -1 wraps to MIN (the reference panics)
         return (T)(a / b);
@@ -238,6 +241,11 @@ __device__ __forceinline__ long long acc_add<long long>(long long a, long long b
 {
     return (long long)((unsigned long long)a + (unsigned long long)b);
 }
+template <>
+__device__ __forceinline__ unsigned long long acc_add<unsigned long long>(unsigned long long a, unsigned long long b)
+{
+    return a + b;  // u64 sums wrap as unsigned and the mean divides unsigned
+}
 
 template <typename T, typename ACC>
 __device__ __forceinline__ ACC to_acc(T v) { return (ACC)v; }
@@ -264,8 +272,39 @@ __device__ __forceinline__ ACC block_tree(ACC s)
     return v;  // valid in warp 0
 }
 
-template <typename T, typename ACC, bool ALIGNED, int UNROLL>
-__global__ void __launch_bounds__(kThreads) sum_pass1_kernel(const T *in, size_t n, size_t chunk, ACC *partials)
+// cross-GPU exchange of the rank totals through peer-mapped memory (see sum_kernel)
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+template <typename ACC>
+__device__ __forceinline__ ACC ld_partial(const ACC *p)
+{
+    return *reinterpret_cast<const volatile ACC *>(p);  // written by other blocks of this launch: never from L1
+}
+
+// ONE launch per sum.  Every block reduces its chunk (pass 1) and publishes the partial; the block that takes the
+// last ticket of a device counter folds all partials (pass 2) — in INDEX order, whichever block that happens to be,
+// so the result does not depend on block scheduling — and, in the multi-GPU form (XCHG), also exchanges the rank's
+// total with the peers:
+//   every rank owns a small exchange buffer that all peers map (CUDA IPC).  Threads 0..R-1 of the last block each
+//   publish the total into one peer's buffer with a system-scope release store (R NVLink stores in flight), wait
+//   for the R totals addressed to this rank with acquire loads, and thread 0 folds them in RANK order: all ranks
+//   end with identical bits.  Slots are double buffered by the parity of the call number: a rank can only be one
+//   call ahead of a peer (it needs the peer's value to finish a call), so parity p of call k+2 is never written
+//   before every rank has finished reading parity p of call k.  A peer that does not arrive within
+//   `timeout_cycles` makes the kernel store the call number to `status` (host-mapped memory) instead of hanging
+//   the GPU; the host reports it as an error at the next synchronisation point (cb_comm_check).
+// divisor > 0: mean = sum / (ACC)divisor, one IEEE division (integers: truncating)
+template <typename T, typename ACC, bool ALIGNED, int UNROLL, bool XCHG>
+__global__ void __launch_bounds__(kThreads)
+sum_kernel(const T *in, size_t n, size_t chunk, ACC *partials, unsigned int *ticket, ACC *out, size_t divisor, XchgArgs x)
 {
     constexpr int VEC = 16 / sizeof(T);
     const size_t begin = (size_t)blockIdx.x * chunk;
@@ -306,17 +345,65 @@ __global__ void __launch_bounds__(kThreads) sum_pass1_kernel(const T *in, size_t
 #pragma unroll
     for (int j = 1; j < VEC; j++) s = acc_add<ACC>(s, acc[j]);
     s = block_tree<ACC, kThreads>(s);
-    if (threadIdx.x == 0) partials[blockIdx.x] = s;
-}
 
-// divisor > 0: mean = sum / (ACC)divisor, one IEEE division (integers: truncating)
-template <typename ACC>
-__global__ void __launch_bounds__(kThreads) sum_pass2_kernel(const ACC *partials, int nblocks, ACC *out, size_t divisor)
-{
-    ACC s = (ACC)0;
-    for (int i = threadIdx.x; i < nblocks; i += kThreads) s = acc_add<ACC>(s, partials[i]);
-    s = block_tree<ACC, kThreads>(s);
-    if (threadIdx.x == 0) *out = divisor ? s / (ACC)divisor : s;
+    // publish the partial, then take a ticket: the block holding the last one sees every partial
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = s;
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) *ticket = 0u;  // ready for the next launch (launches on one device are stream ordered)
+
+    // pass 2: thread t folds partials t, t + 256, ... then the same tree
+    ACC t = (ACC)0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) t = acc_add<ACC>(t, ld_partial<ACC>(partials + i));
+    t = block_tree<ACC, kThreads>(t);
+    if (!XCHG) {
+        if (threadIdx.x == 0) *out = divisor ? t / (ACC)divisor : t;
+        return;
+    }
+    __shared__ ACC vals[kMaxRanks];
+    __shared__ ACC local;
+    if (threadIdx.x == 0) local = t;
+    __syncthreads();
+    const int parity = (int)(x.epoch & 1ull);
+    if ((int)threadIdx.x < x.n_ranks) {
+        const int r = threadIdx.x;
+        unsigned long long bits = 0;
+        const ACC mine = local;
+        memcpy(&bits, &mine, sizeof(ACC));
+        XchgSlot *dst = x.peers[r] + parity * x.n_ranks + x.rank;  // my slot in rank r's buffer (peer memory)
+        *reinterpret_cast<volatile unsigned long long *>(&dst->value) = bits;
+        st_release_sys(&dst->epoch, x.epoch);
+        const XchgSlot *src = x.peers[x.rank] + parity * x.n_ranks + r;  // rank r's slot in my buffer
+        const long long t0 = clock64();
+        bool ok = true;
+        while (ld_acquire_sys(&src->epoch) != x.epoch) {
+            if (clock64() - t0 > x.timeout_cycles) {  // a peer never arrived: fail instead of hanging the GPU
+                ok = false;
+                break;
+            }
+        }
+        unsigned long long got = *reinterpret_cast<const volatile unsigned long long *>(&src->value);
+        if (!ok) {
+            got = 0;
+            *reinterpret_cast<volatile int *>(x.status) = (int)x.epoch;  // host-mapped: read by cb_comm_check
+            __threadfence_system();
+        }
+        ACC v;
+        memcpy(&v, &got, sizeof(ACC));
+        vals[r] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ACC tot = vals[0];
+        for (int r = 1; r < x.n_ranks; r++) tot = acc_add<ACC>(tot, vals[r]);  // rank order, like fold_ranks_kernel
+        *out = divisor ? tot / (ACC)divisor : tot;
+    }
 }
 
 // rank-ordered fold of the gathered per-rank partials (multi-GPU combine): sequential
@@ -327,73 +414,6 @@ __global__ void fold_ranks_kernel(const ACC *gathered, int n_ranks, ACC *out, si
         ACC s = gathered[0];
         for (int r = 1; r < n_ranks; r++) s = acc_add<ACC>(s, gathered[r]);
         *out = divisor ? s / (ACC)divisor : s;
-    }
-}
-
-// ---- fused pass 2 + cross-GPU exchange over NVLink peer memory -----------------------------------
-// Every rank owns a small exchange buffer that all peers map (CUDA IPC).  The single block that folds
-// the pass-1 partials also publishes the rank's total into every peer's buffer with system-scope
-// release stores (threads 0..R-1 each serve one peer: R NVLink stores in flight), waits for the R
-// totals addressed to this rank with acquire loads, and folds them in rank order.  One kernel instead
-// of pass 2 + ncclAllGather + fold: the exchange costs one NVLink round trip (~2-4 us), not a
-// collective launch.  Slots are double buffered by the parity of the call number: a rank can only be one
-// call ahead of a peer (it needs the peer's value to finish a call), so parity p of call k+2 is never
-// written before every rank has finished reading parity p of call k.
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-template <typename ACC>
-__global__ void __launch_bounds__(kThreads)
-sum_pass2_exchange_kernel(const ACC *partials, int nblocks, XchgSlot *const *peers, int n_ranks, int rank,
-                          unsigned long long epoch, ACC *out, size_t divisor, long long timeout_cycles, int *status)
-{
-    __shared__ ACC vals[kMaxRanks];
-    __shared__ ACC local;
-    ACC s = (ACC)0;
-    for (int i = threadIdx.x; i < nblocks; i += kThreads) s = acc_add<ACC>(s, partials[i]);
-    s = block_tree<ACC, kThreads>(s);
-    if (threadIdx.x == 0) local = s;
-    __syncthreads();
-    const int parity = (int)(epoch & 1ull);
-    if ((int)threadIdx.x < n_ranks) {
-        const int r = threadIdx.x;
-        unsigned long long bits = 0;
-        const ACC mine = local;
-        memcpy(&bits, &mine, sizeof(ACC));
-        XchgSlot *dst = peers[r] + parity * n_ranks + rank;  // my slot in rank r's buffer (peer memory)
-        *reinterpret_cast<volatile unsigned long long *>(&dst->value) = bits;
-        st_release_sys(&dst->epoch, epoch);
-        const XchgSlot *src = peers[rank] + parity * n_ranks + r;  // rank r's slot in my buffer
-        const long long t0 = clock64();
-        bool ok = true;
-        while (ld_acquire_sys(&src->epoch) != epoch) {
-            if (clock64() - t0 > timeout_cycles) {  // a peer never arrived: fail instead of hanging the GPU
-                ok = false;
-                break;
-            }
-        }
-        unsigned long long got = *reinterpret_cast<const volatile unsigned long long *>(&src->value);
-        if (!ok) {
-            got = 0;
-            atomicExch(status, 1);
-        }
-        ACC v;
-        memcpy(&v, &got, sizeof(ACC));
-        vals[r] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        ACC t = vals[0];
-        for (int r = 1; r < n_ranks; r++) t = acc_add<ACC>(t, vals[r]);  // rank order, like fold_ranks_kernel
-        *out = divisor ? t / (ACC)divisor : t;
     }
 }
 
@@ -433,38 +453,41 @@ cudaError_t launch_binary_op(const LaunchCtx &ctx, int op, const void *lhs, cons
     }
 }
 
-template <typename T, typename ACC>
-cudaError_t launch_sum_xchg_t(const LaunchCtx &ctx, const void *in, size_t n, int blocks, size_t chunk, void *partials,
-                              void *out, size_t divisor, const XchgArgs &x)
+template <typename T, typename ACC, bool XCHG>
+cudaError_t launch_sum_t(const LaunchCtx &ctx, const void *in, size_t n, int blocks, size_t chunk, void *partials,
+                         unsigned int *ticket, void *out, size_t divisor, const XchgArgs &x)
 {
-    if (n == 0) {  // an empty slice contributes 0 but still takes part in the exchange
-        cudaError_t e = cudaMemsetAsync(partials, 0, sizeof(ACC), ctx.stream);
-        if (e != cudaSuccess) return e;
-        blocks = 1;
-    } else if (aligned16(in)) {
-        sum_pass1_kernel<T, ACC, true, 4><<<blocks, kThreads, 0, ctx.stream>>>((const T *)in, n, chunk, (ACC *)partials);
-    } else {
-        sum_pass1_kernel<T, ACC, false, 1><<<blocks, kThreads, 0, ctx.stream>>>((const T *)in, n, chunk, (ACC *)partials);
-    }
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    sum_pass2_exchange_kernel<ACC><<<1, kThreads, 0, ctx.stream>>>((const ACC *)partials, blocks, x.peers, x.n_ranks, x.rank,
-                                                                   x.epoch, (ACC *)out, divisor, x.timeout_cycles, x.status);
+    // n == 0 (an empty slice of a sharded buffer): one block, nothing to read, the partial is 0 — the rank still takes
+    // part in the exchange
+    if (n == 0) blocks = 1;
+    if (aligned16(in))
+        sum_kernel<T, ACC, true, 4, XCHG><<<blocks, kThreads, 0, ctx.stream>>>((const T *)in, n, chunk ? chunk : 1, (ACC *)partials,
+                                                                              ticket, (ACC *)out, divisor, x);
+    else
+        sum_kernel<T, ACC, false, 1, XCHG><<<blocks, kThreads, 0, ctx.stream>>>((const T *)in, n, chunk ? chunk : 1, (ACC *)partials,
+                                                                               ticket, (ACC *)out, divisor, x);
     return cudaGetLastError();
 }
 
-template <typename T, typename ACC>
-cudaError_t launch_sum_t(const LaunchCtx &ctx, const void *in, size_t n, int blocks, size_t chunk, void *partials,
-                         void *out, size_t divisor)
+template <bool XCHG>
+cudaError_t launch_sum_dtype(const LaunchCtx &ctx, int dtype, const void *in, size_t n, int blocks, size_t chunk, void *partials,
+                             unsigned int *ticket, void *out, size_t divisor, const XchgArgs &x)
 {
-    if (aligned16(in))
-        sum_pass1_kernel<T, ACC, true, 4><<<blocks, kThreads, 0, ctx.stream>>>((const T *)in, n, chunk, (ACC *)partials);
-    else
-        sum_pass1_kernel<T, ACC, false, 1><<<blocks, kThreads, 0, ctx.stream>>>((const T *)in, n, chunk, (ACC *)partials);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    sum_pass2_kernel<ACC><<<1, kThreads, 0, ctx.stream>>>((const ACC *)partials, blocks, (ACC *)out, divisor);
-    return cudaGetLastError();
+    switch (dtype) {
+    case CB_F32: return launch_sum_t<float, float, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
+    case CB_F64: return launch_sum_t<double, double, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
+    case CB_F16: return launch_sum_t<half_bits, float, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
+    case CB_I32: return launch_sum_t<int, long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
+    case CB_I64: return launch_sum_t<long long, long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
+    case CB_U32: return launch_sum_t<unsigned int, long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
+    case CB_U8: return launch_sum_t<unsigned char, long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
+    case CB_BF16: return launch_sum_t<bf16_bits, float, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
+    case CB_I8: return launch_sum_t<signed char, long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
+    case CB_I16: return launch_sum_t<short, long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
+    case CB_U16: return launch_sum_t<unsigned short, long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
+    case CB_U64: return launch_sum_t<unsigned long long, unsigned long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
+    default: return cudaErrorInvalidValue;
+    }
 }
 
 }  // namespace
@@ -584,51 +607,26 @@ void sum_plan(int dtype, size_t n, int *blocks, size_t *chunk, int *threads, int
     *threads2 = kThreads;
 }
 
-cudaError_t launch_sum(const LaunchCtx &ctx, int dtype, const void *in, size_t n, void *partials, void *out, size_t divisor)
+cudaError_t launch_sum(const LaunchCtx &ctx, int dtype, const void *in, size_t n, void *partials, unsigned int *ticket,
+                       void *out, size_t divisor)
 {
     (void)cudaGetLastError();  // a stale error of an earlier, unchecked call must not be blamed on this launch
     int blocks, threads, vec, threads2;
     size_t chunk;
     sum_plan(dtype, n, &blocks, &chunk, &threads, &vec, &threads2);
-    switch (dtype) {
-    case CB_F32: return launch_sum_t<float, float>(ctx, in, n, blocks, chunk, partials, out, divisor);
-    case CB_F64: return launch_sum_t<double, double>(ctx, in, n, blocks, chunk, partials, out, divisor);
-    case CB_F16: return launch_sum_t<half_bits, float>(ctx, in, n, blocks, chunk, partials, out, divisor);
-    case CB_I32: return launch_sum_t<int, long long>(ctx, in, n, blocks, chunk, partials, out, divisor);
-    case CB_I64: return launch_sum_t<long long, long long>(ctx, in, n, blocks, chunk, partials, out, divisor);
-    case CB_U32: return launch_sum_t<unsigned int, long long>(ctx, in, n, blocks, chunk, partials, out, divisor);
-    case CB_U8: return launch_sum_t<unsigned char, long long>(ctx, in, n, blocks, chunk, partials, out, divisor);
-    case CB_BF16: return launch_sum_t<bf16_bits, float>(ctx, in, n, blocks, chunk, partials, out, divisor);
-    case CB_I8: return launch_sum_t<signed char, long long>(ctx, in, n, blocks, chunk, partials, out, divisor);
-    case CB_I16: return launch_sum_t<short, long long>(ctx, in, n, blocks, chunk, partials, out, divisor);
-    case CB_U16: return launch_sum_t<unsigned short, long long>(ctx, in, n, blocks, chunk, partials, out, divisor);
-    case CB_U64: return launch_sum_t<unsigned long long, long long>(ctx, in, n, blocks, chunk, partials, out, divisor);
-    default: return cudaErrorInvalidValue;
-    }
+    XchgArgs none;
+    memset(&none, 0, sizeof none);
+    return launch_sum_dtype<false>(ctx, dtype, in, n, blocks, chunk, partials, ticket, out, divisor, none);
 }
 
-cudaError_t launch_sum_exchange(const LaunchCtx &ctx, int dtype, const void *in, size_t n, void *partials, void *out,
-                                size_t divisor, const XchgArgs &x)
+cudaError_t launch_sum_exchange(const LaunchCtx &ctx, int dtype, const void *in, size_t n, void *partials, unsigned int *ticket,
+                                void *out, size_t divisor, const XchgArgs &x)
 {
     (void)cudaGetLastError();
     int blocks = 1, threads, vec, threads2;
     size_t chunk = 0;
     if (n) sum_plan(dtype, n, &blocks, &chunk, &threads, &vec, &threads2);
-    switch (dtype) {
-    case CB_F32: return launch_sum_xchg_t<float, float>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
-    case CB_F64: return launch_sum_xchg_t<double, double>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
-    case CB_F16: return launch_sum_xchg_t<half_bits, float>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
-    case CB_I32: return launch_sum_xchg_t<int, long long>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
-    case CB_I64: return launch_sum_xchg_t<long long, long long>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
-    case CB_U32: return launch_sum_xchg_t<unsigned int, long long>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
-    case CB_U8: return launch_sum_xchg_t<unsigned char, long long>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
-    case CB_BF16: return launch_sum_xchg_t<bf16_bits, float>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
-    case CB_I8: return launch_sum_xchg_t<signed char, long long>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
-    case CB_I16: return launch_sum_xchg_t<short, long long>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
-    case CB_U16: return launch_sum_xchg_t<unsigned short, long long>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
-    case CB_U64: return launch_sum_xchg_t<unsigned long long, long long>(ctx, in, n, blocks, chunk, partials, out, divisor, x);
-    default: return cudaErrorInvalidValue;
-    }
+    return launch_sum_dtype<true>(ctx, dtype, in, n, blocks, chunk, partials, ticket, out, divisor, x);
 }
 
 cudaError_t launch_fold_ranks(const LaunchCtx &ctx, int dtype, const void *gathered, int n_ranks, void *out, size_t divisor)
@@ -640,6 +638,10 @@ cudaError_t launch_fold_ranks(const LaunchCtx &ctx, int dtype, const void *gathe
         break;
     case CB_F64:
         fold_ranks_kernel<double><<<1, 32, 0, ctx.stream>>>((const double *)gathered, n_ranks, (double *)out, divisor);
+        break;
+    case CB_U64:
+        fold_ranks_kernel<unsigned long long><<<1, 32, 0, ctx.stream>>>((const unsigned long long *)gathered, n_ranks,
+                                                                       (unsigned long long *)out, divisor);
         break;
     default:
         fold_ranks_kernel<long long><<<1, 32, 0, ctx.stream>>>((const long long *)gathered, n_ranks, (long long *)out, divisor);

@@ -24,7 +24,9 @@ cudaError_t launch_copy(const LaunchCtx &ctx, void *dst, const void *src, size_t
 int launch_copy_count(const void *dst, const void *src, size_t bytes);
 void sum_plan(int dtype, size_t n, int *blocks, size_t *chunk, int *threads, int *vec, int *threads2);
 // partials: device scratch of kSumMaxBlocks accumulators; out: device scalar of the accumulation type
-cudaError_t launch_sum(const LaunchCtx &ctx, int dtype, const void *in, size_t n, void *partials, void *out, size_t divisor);
+// (`ticket`: a zero-initialised device counter owned by the device; the kernel leaves it at zero)
+cudaError_t launch_sum(const LaunchCtx &ctx, int dtype, const void *in, size_t n, void *partials, unsigned int *ticket, void *out,
+                       size_t divisor);
 // cross-GPU exchange of reduction totals through peer-mapped memory (see kernels.cu)
 constexpr int kMaxRanks = 64;
 struct XchgSlot {
@@ -36,10 +38,10 @@ struct XchgArgs {
     int n_ranks, rank;
     unsigned long long epoch;
     long long timeout_cycles;
-    int *status;  // set to 1 by the kernel when a peer never arrived
+    int *status;  // host-mapped flag: the kernel stores the call number here when a peer never arrived
 };
-cudaError_t launch_sum_exchange(const LaunchCtx &ctx, int dtype, const void *in, size_t n, void *partials, void *out,
-                                size_t divisor, const XchgArgs &x);
+cudaError_t launch_sum_exchange(const LaunchCtx &ctx, int dtype, const void *in, size_t n, void *partials, unsigned int *ticket,
+                                void *out, size_t divisor, const XchgArgs &x);
 cudaError_t launch_fold_ranks(const LaunchCtx &ctx, int dtype, const void *gathered, int n_ranks, void *out, size_t divisor);
 
 }  // namespace cb

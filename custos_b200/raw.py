@@ -199,6 +199,8 @@ class RawDevice:
     @staticmethod
     def acc_dtype(dtype):
         dt = dtype_code(dtype)
+        if dt == N.U64:
+            return np.uint64  # u64 sums wrap as unsigned and the mean divides unsigned
         return np.float32 if dt in (N.F32, N.F16, N.BF16) else (np.float64 if dt == N.F64 else np.int64)
 
     def sum(self, dtype, dptr: int, n: int):
@@ -273,6 +275,20 @@ class Comm:
 
     def mean_into(self, dtype, dptr: int, n_local: int, n_global: int, out_dptr: int):
         N.call("cb_comm_mean", self.h, dtype_code(dtype), dptr, n_local, n_global, out_dptr)
+
+    def check(self):
+        """Synchronises and raises if a peer missed an exchange (the device scalar is then not the global sum)."""
+        N.call("cb_comm_check", self.h)
+
+    def sum(self, dtype, dptr: int, n_local: int):
+        out = np.zeros(1, dtype=RawDevice.acc_dtype(dtype))
+        N.call("cb_comm_sum_host", self.h, dtype_code(dtype), dptr, n_local, out.ctypes.data_as(C.c_void_p))
+        return out[0]
+
+    def mean(self, dtype, dptr: int, n_local: int, n_global: int):
+        out = np.zeros(1, dtype=RawDevice.acc_dtype(dtype))
+        N.call("cb_comm_mean_host", self.h, dtype_code(dtype), dptr, n_local, n_global, out.ctypes.data_as(C.c_void_p))
+        return out[0]
 
     def close(self):
         if self.h:

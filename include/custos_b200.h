@@ -193,7 +193,10 @@ int32_t cb_cache_clear(cb_device *dev);
 
 /* Read / WriteBuf::write / alloc_from_slice (src/devices/cuda/ops.rs:17-49,101-105,
  * cuda.rs:124-137).  Host pointers may be pageable; transfers are staged through
- * pinned buffers owned by the device.  cb_d2h synchronises. */
+ * pinned buffers owned by the device.  cb_d2h synchronises.  cb_h2d returns once the source may
+ * be reused: a pageable source has been copied into the staging buffers by then, a PINNED source
+ * (cb_host_alloc) is read by the DMA engine directly, so cb_h2d waits for that copy to finish
+ * (use cb_h2d_async to overlap it and synchronise yourself). */
 int32_t cb_h2d(cb_device *dev, uint64_t dst, const void *src, size_t bytes);
 int32_t cb_d2h(cb_device *dev, void *dst, uint64_t src, size_t bytes);
 /* pinned host memory for zero-copy-staging callers */
@@ -313,6 +316,17 @@ int32_t cb_comm_uses_peer_memory(cb_comm *c, int32_t *flag);
 int32_t cb_comm_sum(cb_comm *c, int32_t dtype, uint64_t in, size_t n_local, uint64_t out);
 int32_t cb_comm_mean(cb_comm *c, int32_t dtype, uint64_t in, size_t n_local, size_t n_global,
                      uint64_t out);
+/* the same, copied to a host scalar of the accumulation type (synchronises) */
+int32_t cb_comm_sum_host(cb_comm *c, int32_t dtype, uint64_t in, size_t n_local, void *host_out);
+int32_t cb_comm_mean_host(cb_comm *c, int32_t dtype, uint64_t in, size_t n_local, size_t n_global,
+                          void *host_out);
+/* Synchronises the device stream and reports a failed exchange: a peer that did not reach a cb_comm_sum / mean
+ * within CB_COMM_TIMEOUT_MS (default 2000) makes the kernel give up instead of hanging the GPU, and the value it
+ * wrote is then NOT the global sum -> CB_ERR_STATE here, from every later cb_comm_* call and from the *_host forms.
+ * Call it before trusting a device scalar written by cb_comm_sum / cb_comm_mean. */
+int32_t cb_comm_check(cb_comm *c);
+int32_t cb_comm_rank(cb_comm *c, int32_t *rank, int32_t *n_ranks);
+int32_t cb_comm_device(cb_comm *c, cb_device **dev);
 /* contiguous slice [begin, end) of rank r out of n_ranks over n elements, 16-byte aligned starts */
 int32_t cb_shard_range(size_t n, int32_t elem_bytes, int32_t n_ranks, int32_t rank,
                        size_t *begin, size_t *end);
