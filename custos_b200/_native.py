@@ -110,6 +110,10 @@ SIGNATURES = {
     "cbm_device_create": [_i32, _u32, _i32, _P(_vp)],
     "cbm_device_destroy": [_vp],
     "cbm_device_raw": [_vp, _P(_vp)],
+    "cbm_device_set_comm": [_vp, _vp],
+    "cbm_buffer_new_sharded": [_vp, _i32, _sz, _P(_u64)],
+    "cbm_buffer_from_host_sharded": [_vp, _i32, _vp, _sz, _P(_u64)],
+    "cbm_buffer_shard": [_vp, _u64, _P(_sz), _P(_sz), _P(_sz)],
     "cbm_buffer_new": [_vp, _i32, _sz, _P(_u64)],
     "cbm_buffer_from_host": [_vp, _i32, _vp, _sz, _P(_u64)],
     "cbm_buffer_drop": [_vp, _u64],

@@ -107,14 +107,15 @@ struct cb_device {
     size_t stage_bytes = 0;
 
     // host-operand pipeline (cb_apply_host): a ring of device chunks and a third stream for D2H
-    static constexpr int kPipeSlots = 3;
+    static constexpr int kPipeSlots = 8;  // capacity; `pipe_slots` (CB_PIPE_SLOTS, default 3) are in use
+    int pipe_slots = 3;
     cudaStream_t d2h_stream = nullptr;
     size_t pipe_chunk_bytes = 0;
-    void *pipe_in[kPipeSlots] = {nullptr, nullptr, nullptr};
-    void *pipe_out[kPipeSlots] = {nullptr, nullptr, nullptr};
-    cudaEvent_t pipe_h2d[kPipeSlots] = {nullptr, nullptr, nullptr};
-    cudaEvent_t pipe_k[kPipeSlots] = {nullptr, nullptr, nullptr};
-    cudaEvent_t pipe_d2h[kPipeSlots] = {nullptr, nullptr, nullptr};
+    void *pipe_in[kPipeSlots] = {};
+    void *pipe_out[kPipeSlots] = {};
+    cudaEvent_t pipe_h2d[kPipeSlots] = {};
+    cudaEvent_t pipe_k[kPipeSlots] = {};
+    cudaEvent_t pipe_d2h[kPipeSlots] = {};
 
     // reduction scratch
     void *sum_partials = nullptr;  // kSumMaxBlocks x 8 bytes

@@ -71,6 +71,8 @@ struct Handle {
     uint64_t ptr = 0;  // storage owned by (or lent to) this handle; 0 for lazily retrieved buffers
     bool lazy = false;
     bool owned = false;  // freed on drop (AllocFlag::None); cached and gradient buffers are not
+    // sharded device: `len` is this rank's slice [shard_begin, shard_begin + len) of a buffer of global_len elements
+    size_t global_len = 0, shard_begin = 0;
 };
 
 enum class OpKind { NoOp, Apply, UnaryGrad, Binary, Apply2, Clear };
@@ -159,6 +161,7 @@ struct CacheSlot {
 
 struct cbm_device {
     cb_device *raw = nullptr;
+    cb_comm *comm = nullptr;  // set by cbm_device_set_comm: buffers are slices, reductions combine over the ranks
     uint32_t mods = 0;
     int32_t dtype = CB_F32;  // the module's `T` (Lazy<Mods, T = f32>, Graph<Mods, T = f32>)
 
@@ -318,9 +321,14 @@ int32_t retrieve(cbm_device *d, int32_t dtype, size_t len, const cbm_buf *parent
     if (len == 0) return fail(CB_ERR_ZERO_LENGTH, "retrieve: zero length buffer");
     std::vector<uint64_t> parent_ids;
     bool any_requires_grad = false;
+    size_t global_len = 0, shard_begin = 0;
     for (int32_t i = 0; i < n_parents; i++) {
         GET_HANDLE(p, d, parents[i]);
         parent_ids.push_back(p->id);
+        if (p->global_len && p->len == len) {  // an element-wise result of a slice is the same slice of the result
+            global_len = p->global_len;
+            shard_begin = p->shard_begin;
+        }
         auto it = d->requires_grad.find(p->id);
         any_requires_grad = any_requires_grad || (it != d->requires_grad.end() && it->second);
     }
@@ -328,6 +336,8 @@ int32_t retrieve(cbm_device *d, int32_t dtype, size_t len, const cbm_buf *parent
     Handle h;
     h.len = len;
     h.dtype = dtype;
+    h.global_len = global_len;
+    h.shard_begin = shard_begin;
     const uint64_t used_cursor = d->cursor;
     if (d->has(CBM_LAZY)) {
         // Lazy::retrieve: no allocation, the id is the cursor (lazy.rs:325-387)
@@ -509,6 +519,70 @@ extern "C" int32_t cbm_device_raw(cbm_device *d, cb_device **raw)
 {
     CB_CHECK_ARG(d && raw, "null argument");
     *raw = d->raw;
+    return CB_OK;
+}
+
+// ---- sharded device: one process per GPU, every buffer a contiguous slice ------------------------------------------
+// The reference is one device per `CUDA::new` (src/devices/cuda/cuda.rs:53-67; its cross-device test is ignored,
+// :187-202), so this is new.  Element-wise ops, fused chains and gradients are independent per element: each rank
+// runs the unchanged operator API on its slice and never talks to a peer.  Only sum / mean combine — through the
+// communicator's fused reduce + exchange kernel, with identical bits on every rank.
+extern "C" int32_t cbm_device_set_comm(cbm_device *d, cb_comm *comm)
+{
+    CB_CHECK_ARG(d, "null device");
+    if (comm) {
+        cb_device *cd = nullptr;
+        CB_TRY(cb_comm_device(comm, &cd));
+        if (cd != d->raw) return fail(CB_ERR_INVALID_ARG, "the communicator belongs to another device (create it on cbm_device_raw)");
+    }
+    d->comm = comm;
+    return CB_OK;
+}
+
+static int32_t shard_of(cbm_device *d, int32_t dtype, size_t global_len, size_t *begin, size_t *end)
+{
+    if (!d->comm) return fail(CB_ERR_STATE, "not a sharded device: call cbm_device_set_comm first");
+    if (!valid_dtype(dtype)) return fail(CB_ERR_INVALID_ARG, "invalid dtype %d", dtype);
+    int32_t rank = 0, n_ranks = 1;
+    CB_TRY(cb_comm_rank(d->comm, &rank, &n_ranks));
+    CB_TRY(cb_shard_range(global_len, (int32_t)dtype_size(dtype), n_ranks, rank, begin, end));
+    if (*end <= *begin)
+        return fail(CB_ERR_ZERO_LENGTH, "a buffer of %zu elements leaves rank %d of %d without a slice", global_len, rank, n_ranks);
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_buffer_new_sharded(cbm_device *d, int32_t dtype, size_t global_len, cbm_buf *out)
+{
+    CB_CHECK_ARG(d && out, "null argument");
+    size_t b = 0, e = 0;
+    CB_TRY(shard_of(d, dtype, global_len, &b, &e));
+    CB_TRY(cbm_buffer_new(d, dtype, e - b, out));
+    Handle *h = d->handle(*out);
+    h->global_len = global_len;
+    h->shard_begin = b;
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_buffer_from_host_sharded(cbm_device *d, int32_t dtype, const void *global_data, size_t global_len,
+                                                cbm_buf *out)
+{
+    CB_CHECK_ARG(d && out && global_data, "null argument");
+    size_t b = 0, e = 0;
+    CB_TRY(shard_of(d, dtype, global_len, &b, &e));
+    CB_TRY(cbm_buffer_from_host(d, dtype, static_cast<const char *>(global_data) + b * dtype_size(dtype), e - b, out));
+    Handle *h = d->handle(*out);
+    h->global_len = global_len;
+    h->shard_begin = b;
+    return CB_OK;
+}
+
+extern "C" int32_t cbm_buffer_shard(cbm_device *d, cbm_buf b, size_t *begin, size_t *end, size_t *global_len)
+{
+    CB_CHECK_ARG(d, "null device");
+    GET_HANDLE(h, d, b);
+    if (begin) *begin = h->global_len ? h->shard_begin : 0;
+    if (end) *end = (h->global_len ? h->shard_begin : 0) + h->len;
+    if (global_len) *global_len = h->global_len ? h->global_len : h->len;
     return CB_OK;
 }
 
@@ -869,7 +943,10 @@ extern "C" int32_t cbm_clone_buf(cbm_device *d, cbm_buf src, cbm_buf *out)
     CB_TRY(storage_of(d, hs, &es));
     const int32_t dtype = hs->dtype;
     cbm_buf nb = 0;
+    const size_t global_len = hs->global_len, shard_begin = hs->shard_begin;
     CB_TRY(cbm_buffer_new(d, dtype, es.len, &nb));  // CloneBuf (src/devices/cuda/cuda.rs:152-164)
+    d->handle(nb)->global_len = global_len;
+    d->handle(nb)->shard_begin = shard_begin;
     CB_TRY(cb_copy(d->raw, dtype, d->handle(nb)->ptr, 0, es.ptr, 0, es.len));
     *out = nb;
     return CB_OK;
@@ -881,6 +958,8 @@ extern "C" int32_t cbm_sum(cbm_device *d, cbm_buf b, void *host_out)
     GET_HANDLE(h, d, b);
     Entry e;
     CB_TRY(storage_of(d, h, &e));
+    if (d->comm && h->global_len)  // the rank's partial, then ONE exchange of a scalar per rank (rank-ordered fold)
+        return cb_comm_sum_host(d->comm, h->dtype, e.ptr, e.len, host_out);
     return cb_sum_host(d->raw, h->dtype, e.ptr, e.len, host_out);
 }
 
@@ -890,6 +969,7 @@ extern "C" int32_t cbm_mean(cbm_device *d, cbm_buf b, void *host_out)
     GET_HANDLE(h, d, b);
     Entry e;
     CB_TRY(storage_of(d, h, &e));
+    if (d->comm && h->global_len) return cb_comm_mean_host(d->comm, h->dtype, e.ptr, e.len, h->global_len, host_out);
     return cb_mean_host(d->raw, h->dtype, e.ptr, e.len, host_out);
 }
 
@@ -1318,6 +1398,8 @@ extern "C" int32_t cbm_grad(cbm_device *d, cbm_buf b, cbm_buf *grad)
     gh.len = g->len;
     gh.dtype = g->dtype;
     gh.owned = false;  // owned by the gradient pool
+    gh.global_len = h->global_len;
+    gh.shard_begin = h->shard_begin;
     d->buffers[gh.id] = *g;
     *grad = d->new_handle(gh);
     d->grad_handle[id] = *grad;

@@ -49,6 +49,12 @@ class Buffer:
         N.call("cbm_buffer_ptr", self.device.h, self.handle, C.byref(v))
         return v.value
 
+    def shard(self):
+        """(begin, end, global_len): the slice of the global buffer this rank holds."""
+        b, e, g = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        N.call("cbm_buffer_shard", self.device.h, self.handle, C.byref(b), C.byref(e), C.byref(g))
+        return b.value, e.value, g.value
+
     def replace(self) -> "Buffer":
         """Buffer::replace (src/modules/lazy.rs:430-455): reads always resolve by id."""
         return self
@@ -168,12 +174,42 @@ class CUDA:
         self.raw = RawDevice.from_handle(raw)
 
     def close(self):
+        if getattr(self, "comm", None) is not None:
+            N.call("cbm_device_set_comm", self.h, None)
+            self.comm.close()
+            self.comm = None
         if self.h:
             N.call("cbm_device_destroy", self.h)
             self.h = None
 
     def __enter__(self):
         return self
+
+    # ------------------------------------------------------------ sharded device (one process per GPU)
+    def shard(self, n_ranks: int, rank: int, unique_id: bytes) -> "CUDA":
+        """Makes this device one rank of a sharded device: `buffer_sharded` / `new_buffer_sharded` hand out the
+        rank's contiguous slice, every operator works on the slice unchanged, `sum` / `mean` return the global value
+        (one scalar per rank exchanged over NVLink, folded in rank order — identical bits on every rank)."""
+        from .raw import Comm
+        self.comm = Comm(self.raw, n_ranks, rank, unique_id)
+        N.call("cbm_device_set_comm", self.h, self.comm.h)
+        return self
+
+    def buffer_sharded(self, global_data, dtype=None) -> Buffer:
+        """`global_data` is the whole array; only this rank's slice is uploaded."""
+        if dtype is None:
+            dtype = global_data.dtype if isinstance(global_data, np.ndarray) else np.float32
+        dt = dtype_code(dtype)
+        arr = np.ascontiguousarray(global_data, NP_DTYPE[dt])
+        out = C.c_uint64()
+        N.call("cbm_buffer_from_host_sharded", self.h, dt, arr.ctypes.data_as(C.c_void_p), arr.size, C.byref(out))
+        return Buffer(self, out.value, dt)
+
+    def new_buffer_sharded(self, dtype, global_length: int) -> Buffer:
+        dt = dtype_code(dtype)
+        out = C.c_uint64()
+        N.call("cbm_buffer_new_sharded", self.h, dt, global_length, C.byref(out))
+        return Buffer(self, out.value, dt)
 
     def __exit__(self, *a):
         self.close()

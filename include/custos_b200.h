@@ -350,6 +350,21 @@ int32_t cbm_device_create(int32_t ordinal, uint32_t modules, int32_t dtype, cbm_
 int32_t cbm_device_destroy(cbm_device *d);
 int32_t cbm_device_raw(cbm_device *d, cb_device **raw);
 
+/* Sharded device (one process per GPU; the reference is single-device, src/devices/cuda/cuda.rs:53-67,187-202).
+ * After cbm_device_set_comm (the communicator must have been created on cbm_device_raw(d)) the *_sharded
+ * constructors give every rank the contiguous slice cb_shard_range assigns it; every operator of this header then
+ * works on the slice unchanged and without communication, results inherit the slice of their parents, and
+ * cbm_sum / cbm_mean of a sharded buffer return the GLOBAL value — the rank's deterministic partial, one scalar per
+ * rank exchanged over NVLink, folded in rank order: identical bits on every rank.  All ranks must call cbm_sum /
+ * cbm_mean of sharded buffers in the same order (they are collective). */
+int32_t cbm_device_set_comm(cbm_device *d, cb_comm *comm);
+int32_t cbm_buffer_new_sharded(cbm_device *d, int32_t dtype, size_t global_len, cbm_buf *out);
+/* `global_data` is the whole host array (global_len elements); only this rank's slice is read and uploaded */
+int32_t cbm_buffer_from_host_sharded(cbm_device *d, int32_t dtype, const void *global_data, size_t global_len,
+                                     cbm_buf *out);
+/* [begin, end) of the global buffer this handle holds, and the global length (an unsharded buffer: [0, len), len) */
+int32_t cbm_buffer_shard(cbm_device *d, cbm_buf b, size_t *begin, size_t *end, size_t *global_len);
+
 /* Buffer::new / device.buffer([..]) (src/buffer.rs:80-93): allocated immediately, zeroed */
 int32_t cbm_buffer_new(cbm_device *d, int32_t dtype, size_t len, cbm_buf *out);
 int32_t cbm_buffer_from_host(cbm_device *d, int32_t dtype, const void *data, size_t len, cbm_buf *out);
