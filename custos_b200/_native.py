@@ -72,6 +72,8 @@ SIGNATURES = {
     "cb_fill": [_vp, _i32, _u64, _sz, _dbl, _i64],
     "cb_expr_compile": [_vp, _i32, _i32, _progs, _P(_i32), _i32, _P(_vp)],
     "cb_expr_release": [_vp],
+    "cb_expr_set_lookup": [_vp, _i32],
+    "cb_expr_has_lookup": [_vp, _P(_i32)],
     "cb_apply": [_vp, _vp, _u64, _u64, _sz],
     "cb_unary_grad": [_vp, _vp, _u64, _u64, _u64, _sz],
     "cb_unary_grad_ex": [_vp, _vp, _u64, _u64, _u64, _sz, _u32],
@@ -144,6 +146,7 @@ SIGNATURES = {
     "cbm_alloc_later": [_vp],
     "cbm_set_lazy_enabled": [_vp, _i32],
     "cbm_op_hint_src": [_vp, _sz, C.c_char_p, _sz],
+    "cbm_op_expr": [_vp, _sz, _P(_vp)],
     "cbm_set_graph_replay": [_vp, _i32],
     "cbm_replay_kernel_nodes": [_vp, _P(_sz)],
     "cbm_optimize_mem_graph": [_vp],

@@ -29,6 +29,10 @@ struct cb_expr {
     int resident_scalar = 0;  // the persistent grid is exactly one wave of them
     size_t cubin_bytes = 0;
     std::string ir;  // canonical bytes of (dtype, kind, programs): identity of the cached kernel
+    // f16 / bf16 apply expressions: the chain's value for every one of the 65 536 inputs (128 KiB on the device),
+    // filled by this expression's own arithmetic kernel; 0 = no table
+    uint64_t lut = 0;
+    bool lut_enabled = true;  // cb_expr_set_lookup
 };
 
 struct cb_graph {
@@ -54,6 +58,8 @@ struct Tunables {
     int neg_xor = 0;    // CB_NEG_XOR=1: f32 pair neg flips the sign bits on the integer pipe (no gain measured)
     int fuse_scale_add = 1;  // CB_FUSE_SCALE_ADD: (u * 2^k) + C and (u + C) * 2^k become one exact fma in the f32 pair path
     int h_native = 1;  // CB_H_NATIVE: f16 add / sub / mul as single HFMA2s on packed halves
+    int lut16 = 1;     // CB_LUT16: f16 / bf16 unary chains on large buffers run as a shared-memory table lookup
+    long long lut16_min_elems = 1ll << 22;  // CB_LUT16_MIN_ELEMS: shorter buffers keep the arithmetic kernel
     std::string ld_mod = ".cs";
     std::string st_mod = ".cs";
     std::string dump_dir;  // CB_DUMP_DIR: write generated sources and cubins here
@@ -119,6 +125,7 @@ struct cb_device {
 
     // reduction scratch
     void *sum_partials = nullptr;  // kSumMaxBlocks x 8 bytes
+    unsigned long long *lut_counters = nullptr;  // tile / finished-block counters of lut16_kernel, zero between launches
     unsigned int *sum_ticket = nullptr;  // device counter of the one-launch sum (last block folds); zero between launches
     void *sum_scalar = nullptr;    // 8 bytes device
     void *sum_host = nullptr;      // 8 bytes pinned

@@ -417,6 +417,81 @@ __global__ void fold_ranks_kernel(const ACC *gathered, int n_ranks, ACC *out, si
     }
 }
 
+// ------------------------------------------------------------------ 16-bit unary chains as a table lookup
+// A fused unary chain over f16 / bf16 is a function of one 16-bit value: 65 536 possible inputs.  Evaluated with
+// arithmetic it follows the reference — f32 math and a round to 16 bits after EVERY op (src/number.rs:543-676) —
+// and is bound by the FP32 pipe at ~0.46 of the 16-bit HBM roofline (profiles/r1_half_kernels_ncu.md).  The table
+// is filled ONCE per compiled chain by running that very arithmetic kernel over all 65 536 bit patterns, so a
+// lookup returns bit for bit what the arithmetic kernel would have computed, NaN patterns included.
+//  * the 128 KiB table lives in shared memory (one persistent 1024-thread block per SM; 228 KB per SM on B200);
+//  * 128-bit streaming loads / stores, 8 lookups (LDS.U16) per 16-byte unit;
+//  * tiles are handed out by a device counter, so an SM that runs slower (or starts later) simply takes fewer tiles;
+//    the block that finishes last resets the counters for the next launch.
+constexpr int kLutThreads = 1024;
+constexpr int kLutUnroll = 4;
+constexpr size_t kLutBytes = 65536 * 2;
+
+__global__ void iota16_kernel(unsigned short *out)
+{
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 65536u) out[i] = (unsigned short)i;
+}
+
+__device__ __forceinline__ unsigned int lut2(const unsigned short *lut, unsigned int w)
+{
+    const unsigned int lo = lut[w & 0xffffu], hi = lut[w >> 16];
+    unsigned int r;
+    asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ uint4 lut8(const unsigned short *lut, uint4 q)
+{
+    return make_uint4(lut2(lut, q.x), lut2(lut, q.y), lut2(lut, q.z), lut2(lut, q.w));
+}
+
+__global__ void __launch_bounds__(kLutThreads, 1)
+lut16_kernel(const unsigned short *in, unsigned short *out, size_t n, const uint4 *table, unsigned long long *counters)
+{
+    extern __shared__ uint4 lut_q[];
+    for (int i = threadIdx.x; i < (int)(kLutBytes / 16); i += kLutThreads) lut_q[i] = table[i];
+    __shared__ unsigned long long next_tile;
+    __syncthreads();
+    const unsigned short *lut = reinterpret_cast<const unsigned short *>(lut_q);
+    const size_t nunits = n / 8;
+    const size_t tile_units = (size_t)kLutThreads * kLutUnroll;
+    const size_t ntiles = nunits / tile_units;
+    const uint4 *pin = reinterpret_cast<const uint4 *>(in);
+    uint4 *pout = reinterpret_cast<uint4 *>(out);
+    size_t tile = blockIdx.x;  // the first tile is static, the rest come from the counter
+    while (tile < ntiles) {
+        const size_t base = tile * tile_units + threadIdx.x;
+        uint4 r[kLutUnroll];
+#pragma unroll
+        for (int u = 0; u < kLutUnroll; u++) r[u] = ld16(pin + base + (size_t)u * kLutThreads);
+        if (threadIdx.x == 0) next_tile = atomicAdd(&counters[0], 1ull) + gridDim.x;
+#pragma unroll
+        for (int u = 0; u < kLutUnroll; u++) st16(pout + base + (size_t)u * kLutThreads, lut8(lut, r[u]));
+        __syncthreads();
+        tile = next_tile;
+        __syncthreads();
+    }
+    // ragged end: units that do not fill a tile, then the < 8 element tail
+    const size_t gid = (size_t)blockIdx.x * kLutThreads + threadIdx.x;
+    const size_t gsz = (size_t)gridDim.x * kLutThreads;
+    for (size_t u = ntiles * tile_units + gid; u < nunits; u += gsz) st16(pout + u, lut8(lut, ld16(pin + u)));
+    for (size_t i = nunits * 8 + gid; i < n; i += gsz) out[i] = lut[in[i]];
+    // the last block to get here leaves the counters at zero for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&counters[1], 1ull) == gridDim.x - 1) {
+            counters[0] = 0ull;
+            counters[1] = 0ull;
+            __threadfence();
+        }
+    }
+}
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 inline int grid_for(size_t work_items, size_t per_block, int max_blocks)
@@ -627,6 +702,30 @@ cudaError_t launch_sum_exchange(const LaunchCtx &ctx, int dtype, const void *in,
     size_t chunk = 0;
     if (n) sum_plan(dtype, n, &blocks, &chunk, &threads, &vec, &threads2);
     return launch_sum_dtype<true>(ctx, dtype, in, n, blocks, chunk, partials, ticket, out, divisor, x);
+}
+
+cudaError_t launch_iota16(const LaunchCtx &ctx, void *out)
+{
+    (void)cudaGetLastError();
+    iota16_kernel<<<65536 / 256, 256, 0, ctx.stream>>>((unsigned short *)out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lut16(const LaunchCtx &ctx, int sm_count, const void *in, void *out, size_t n, const void *table,
+                         unsigned long long *counters)
+{
+    (void)cudaGetLastError();
+    static bool configured = false;  // per process; the attribute is per function and context-independent for static kernels
+    cudaError_t e = cudaFuncSetAttribute(lut16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+    (void)configured;
+    const size_t tiles = n / 8 / ((size_t)kLutThreads * kLutUnroll);
+    int grid = sm_count;
+    if ((size_t)grid > tiles + 1) grid = (int)(tiles + 1);
+    lut16_kernel<<<grid, kLutThreads, kLutBytes, ctx.stream>>>((const unsigned short *)in, (unsigned short *)out, n,
+                                                              (const uint4 *)table, counters);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_fold_ranks(const LaunchCtx &ctx, int dtype, const void *gathered, int n_ranks, void *out, size_t divisor)

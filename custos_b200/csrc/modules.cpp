@@ -1060,6 +1060,17 @@ extern "C" int32_t cbm_op_hint_src(cbm_device *d, size_t i, char *out, size_t ca
     return CB_OK;
 }
 
+// the compiled kernel behind recorded op i (after the fusing passes): lets a caller hand the SAME fused chain to
+// cb_apply_host for host-resident operands
+extern "C" int32_t cbm_op_expr(cbm_device *d, size_t i, cb_expr **out)
+{
+    CB_CHECK_ARG(d && out, "bad argument");
+    *out = nullptr;
+    if (i >= d->ops.size()) return fail(CB_ERR_INVALID_ARG, "op index %zu out of range (%zu ops)", i, d->ops.size());
+    *out = d->ops[i].expr;  // null for no-ops and the AOT kernels (binary, clear)
+    return CB_OK;
+}
+
 extern "C" int32_t cbm_set_graph_replay(cbm_device *d, int32_t enabled)
 {
     CB_CHECK_ARG(d, "null device");

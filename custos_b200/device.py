@@ -355,6 +355,14 @@ class CUDA:
         N.call("cbm_op_hint_src", self.h, i, buf, len(buf))
         return buf.value.decode()
 
+    def op_expr(self, i: int):
+        """The compiled kernel behind recorded op i (after the fusing passes), usable with RawDevice.apply / apply_host;
+        None for no-ops and the ahead-of-time kernels."""
+        from .raw import Expr
+        h = C.c_void_p()
+        N.call("cbm_op_expr", self.h, i, C.byref(h))
+        return Expr(h, None, N.KERNEL_APPLY) if h.value else None
+
     def set_graph_replay(self, enabled: bool) -> None:
         N.call("cbm_set_graph_replay", self.h, 1 if enabled else 0)
 

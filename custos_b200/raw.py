@@ -18,7 +18,7 @@ class Expr:
     """A compiled (chain of) expression(s): one fused sm_100a kernel."""
 
     def __init__(self, handle, chain: Chain, kind: int):
-        self.handle, self.chain, self.kind, self.dtype = handle, chain, kind, chain.dtype
+        self.handle, self.chain, self.kind, self.dtype = handle, chain, kind, (chain.dtype if chain is not None else None)
 
 
 class Event:
@@ -176,6 +176,15 @@ class RawDevice:
         h = C.c_void_p()
         N.call("cb_expr_compile", self.h, chain.dtype, kind, chain.progs, chain.n_nodes, chain.n_progs, C.byref(h))
         return Expr(h, chain, kind)
+
+    def set_lut(self, e: Expr, enabled: bool):
+        """f16 / bf16 chains: allow / forbid the table-lookup kernel for this expression (cb_expr_set_lookup)."""
+        N.call("cb_expr_set_lookup", e.handle, 1 if enabled else 0)
+
+    def has_lut(self, e: Expr) -> bool:
+        v = C.c_int32()
+        N.call("cb_expr_has_lookup", e.handle, C.byref(v))
+        return bool(v.value)
 
     def apply(self, e: Expr, src: int, dst: int, n: int):
         N.call("cb_apply", self.h, e.handle, src, dst, n)

@@ -224,6 +224,12 @@ int32_t cb_expr_compile(cb_device *dev, int32_t dtype, int32_t kind,
                         const cb_node *const *progs, const int32_t *n_nodes, int32_t n_progs,
                         cb_expr **out);
 int32_t cb_expr_release(cb_expr *e);   /* expressions are owned by the device cache; no-op kept for symmetry */
+/* f16 / bf16 apply expressions carry a 65 536-entry table of the chain's results (filled by the expression's own
+ * arithmetic kernel at compile time); cb_apply of >= CB_LUT16_MIN_ELEMS (2^22) 16-byte-aligned elements runs as a
+ * shared-memory table lookup — same bits, HBM-bound instead of FP32-pipe-bound.  Off per expression with
+ * cb_expr_set_lookup(e, 0), off for the process with CB_LUT16=0. */
+int32_t cb_expr_set_lookup(cb_expr *e, int32_t enabled);
+int32_t cb_expr_has_lookup(cb_expr *e, int32_t *flag);
 
 /* ApplyFunction::apply_fn body (src/devices/cuda/ops.rs:144-177) and the fused
  * chain body (src/devices/cuda/fusing.rs:28-49): out[i] = f(in[i]). */
@@ -415,6 +421,8 @@ int32_t cbm_alloc_later(cbm_device *d);
 int32_t cbm_set_lazy_enabled(cbm_device *d, int32_t enabled);
 /* op hint of recorded op i as reference source ("sin(x)"), "" if none (src/op_hint.rs:44-83) */
 int32_t cbm_op_hint_src(cbm_device *d, size_t i, char *out, size_t cap);
+/* the compiled expression behind recorded op i after the fusing passes (NULL for no-ops and the AOT kernels) */
+int32_t cbm_op_expr(cbm_device *d, size_t i, cb_expr **out);
 /* replay through one captured CUDA graph instead of re-launching (src/devices/cuda/lazy.rs:31-49) */
 int32_t cbm_set_graph_replay(cbm_device *d, int32_t enabled);
 int32_t cbm_replay_kernel_nodes(cbm_device *d, size_t *n);

@@ -413,6 +413,69 @@ int orc_apply_chain_mt(int dtype, const orc_node *const *progs, const int *n_nod
     return ORC_OK;
 }
 
+/* ------------------------------------------------- the two CPU baselines SURVEY.md §8(d) names, for f32
+ * (i)  the FAITHFUL fused path: CPU::unary_fuse_op (src/devices/cpu/cpu_device.rs:217-229) walks the elements and,
+ *      PER ELEMENT AND PER OP, calls the op hint, which builds the op's expression and boxes it —
+ *      `let op: Box<dyn TwoWay<T>> = Box::new(op(x));` (src/op_hint.rs:30-33) — then `.eval()`s it through the vtable and
+ *      drops the box.  Restated: one heap allocation, one indirect call and one free per op per element; the
+ *      arithmetic inside `eval` is the monomorphised expression (here: the evaluator specialised by a switch on the
+ *      program's root — programs are walked, not re-validated).
+ * (ii) the MONOMORPHISED unfused path: apply_fn_slice (src/devices/cpu_stack_ops.rs:7-15) once per recorded op, each a
+ *      tight loop over the whole buffer (n_progs passes over memory).
+ * Both produce the bits of orc_apply_chain (tests/test_oracle_kat.py). */
+struct boxed_op {
+    float (*eval)(const struct boxed_op *self); /* the vtable slot */
+    const orc_node *nd;
+    int n;
+    float val; /* Resolve { val, marker } */
+};
+static float boxed_eval(const struct boxed_op *self) { return eval_f32(self->nd, self->n, self->val, 0.f); }
+
+int orc_apply_chain_boxed_f32(const orc_node *const *progs, const int *n_nodes, int n_progs, const float *x, float *out,
+                              size_t len)
+{
+    for (int k = 0; k < n_progs; k++) {
+        int rc = check_dtype_prog(ORC_F32, progs[k], n_nodes[k]);
+        if (rc) return rc;
+    }
+    for (size_t i = 0; i < len; i++) {
+        float cur = x[i];
+        for (int k = 0; k < n_progs; k++) {
+            struct boxed_op *volatile op = (struct boxed_op *)malloc(sizeof(struct boxed_op)); /* Box::new(op(resolve)) */
+            if (!op) return ORC_ERR_ARG;
+            op->eval = boxed_eval;
+            op->nd = progs[k];
+            op->n = n_nodes[k];
+            op->val = cur;
+            cur = op->eval(op); /* dyn TwoWay::eval */
+            free((void *)op);   /* the box is dropped */
+        }
+        out[i] = cur;
+    }
+    return ORC_OK;
+}
+
+int orc_apply_chain_unfused_f32(const orc_node *const *progs, const int *n_nodes, int n_progs, const float *x, float *out,
+                                size_t len)
+{
+    for (int k = 0; k < n_progs; k++) {
+        int rc = check_dtype_prog(ORC_F32, progs[k], n_nodes[k]);
+        if (rc) return rc;
+    }
+    float *tmp = (float *)malloc(len * sizeof(float) + 4);
+    if (!tmp) return ORC_ERR_ARG;
+    const float *src = x;
+    for (int k = 0; k < n_progs; k++) {
+        float *dst = (k == n_progs - 1) ? out : ((k & 1) ? out : tmp); /* a new buffer per op in the reference */
+        if (dst == src) dst = (dst == out) ? tmp : out;
+        for (size_t i = 0; i < len; i++) dst[i] = eval_f32(progs[k], n_nodes[k], src[i], 0.f);
+        src = dst;
+    }
+    if (src != out) memcpy(out, src, len * sizeof(float));
+    free(tmp);
+    return ORC_OK;
+}
+
 /* cpu_stack_ops.rs:18-30: `*lhs_grad += *out * lhs_grad_fn((*lhs).to_val()).eval();`
  * — a multiply, then an add, each rounded (no FMA). */
 int orc_add_unary_grad(int dtype, const orc_node *nodes, int n, const void *lhs, const void *out_grad,

@@ -62,6 +62,14 @@ int orc_apply_chain(int dtype, const orc_node *const *progs, const int *n_nodes,
 /* same, split over `threads` OS threads (NOT what the reference does; labelled in bench output) */
 int orc_apply_chain_mt(int dtype, const orc_node *const *progs, const int *n_nodes, int n_progs,
                        const void *x, void *out, size_t len, int threads);
+/* f32 only — the two single-threaded CPU baselines of SURVEY.md §8(d): (i) the fused path as the reference runs it, a
+ * heap-boxed dyn op built, evaluated and dropped per element and per op (src/devices/cpu/cpu_device.rs:217-229,
+ * src/op_hint.rs:30-33); (ii) one apply_fn_slice loop per recorded op (src/devices/cpu_stack_ops.rs:7-15).  Same bits
+ * as orc_apply_chain. */
+int orc_apply_chain_boxed_f32(const orc_node *const *progs, const int *n_nodes, int n_progs, const float *x, float *out,
+                              size_t len);
+int orc_apply_chain_unfused_f32(const orc_node *const *progs, const int *n_nodes, int n_progs, const float *x, float *out,
+                                size_t len);
 /* add_unary_grad (src/devices/cpu_stack_ops.rs:18-30): lhs_grad += out * g(lhs) */
 int orc_add_unary_grad(int dtype, const orc_node *nodes, int n, const void *lhs, const void *out_grad,
                        void *lhs_grad, size_t len);

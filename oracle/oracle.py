@@ -54,6 +54,8 @@ def lib() -> C.CDLL:
         L.orc_apply_fn.argtypes = [i32, nodes, i32, vp, vp, sz]
         L.orc_apply_chain.argtypes = [i32, progs, C.POINTER(C.c_int), i32, vp, vp, sz]
         L.orc_apply_chain_mt.argtypes = [i32, progs, C.POINTER(C.c_int), i32, vp, vp, sz, i32]
+        L.orc_apply_chain_boxed_f32.argtypes = [progs, C.POINTER(C.c_int), i32, vp, vp, sz]
+        L.orc_apply_chain_unfused_f32.argtypes = [progs, C.POINTER(C.c_int), i32, vp, vp, sz]
         L.orc_add_unary_grad.argtypes = [i32, nodes, i32, vp, vp, vp, sz]
         L.orc_apply2.argtypes = [i32, nodes, i32, vp, vp, vp, sz]
         L.orc_binary.argtypes = [i32, i32, vp, vp, vp, sz]
@@ -135,6 +137,25 @@ def apply_chain(fs, dtype, x, threads: int = 1):
         _check(lib().orc_apply_chain(dtype, progs, n_nodes, ch.n_progs, _ptr(x), _ptr(out), x.size))
     else:
         _check(lib().orc_apply_chain_mt(dtype, progs, n_nodes, ch.n_progs, _ptr(x), _ptr(out), x.size, threads))
+    return out
+
+
+def apply_chain_boxed(fs, x):
+    """f32 only: the reference's fused CPU path as it really runs — per element and per op a heap-boxed dyn op is
+    built, evaluated through a function pointer and dropped (cpu_device.rs:217-229, op_hint.rs:30-33)."""
+    ch, progs, n_nodes = _chain(fs, F32)
+    x = _as(F32, x)
+    out = np.empty_like(x)
+    _check(lib().orc_apply_chain_boxed_f32(progs, n_nodes, ch.n_progs, _ptr(x), _ptr(out), x.size))
+    return out
+
+
+def apply_chain_unfused(fs, x):
+    """f32 only: one monomorphised apply_fn_slice loop per recorded op (cpu_stack_ops.rs:7-15), n_progs passes."""
+    ch, progs, n_nodes = _chain(fs, F32)
+    x = _as(F32, x)
+    out = np.empty_like(x)
+    _check(lib().orc_apply_chain_unfused_f32(progs, n_nodes, ch.n_progs, _ptr(x), _ptr(out), x.size))
     return out
 
 

@@ -259,3 +259,43 @@ def test_module_buffers_of_every_new_dtype():
         assert flags.read().tolist() == [True, False, True]
         flags.clear()
         assert flags.read().tolist() == [False] * 3
+
+
+# ------------------------------------------------------------------ 16-bit chains as a table lookup
+@pytest.mark.parametrize("dt", [N.F16, N.BF16])
+@pytest.mark.parametrize("chain_name", ["chain8", "cheap8", "single_tan"])
+def test_large_16bit_buffers_take_the_lookup_kernel_and_match_the_arithmetic_kernel(raw_device, dt, chain_name):
+    """cb_apply switches to lut16_kernel at CB_LUT16_MIN_ELEMS (2^22) elements.  The table is filled by the arithmetic
+    kernel itself, so both paths must agree bit for bit on every one of the 65 536 inputs — NaN patterns included —
+    whatever the buffer length, alignment of the tail, or aliasing of input and output."""
+    dev = raw_device
+    chain = {"chain8": CHAIN8, "cheap8": CHEAP8, "single_tan": [lambda v: v.tan()]}[chain_name]
+    e = dev.compile(chain, dt)
+    n = (1 << 22) + 8 * 1024 * 3 + 5  # whole tiles + ragged units + a scalar tail
+    rng = np.random.default_rng(31)
+    x = np.concatenate([np.arange(65536, dtype=np.uint16), rng.integers(0, 65536, n - 65536).astype(np.uint16)])
+    px, po = dev.upload(x), dev.alloc(n * 2)
+    before = dev.launches
+    dev.apply(e, px, po, n)  # lookup kernel
+    assert dev.launches - before == 1
+    got = dev.d2h(po, n, N.U16)
+    pa = dev.alloc(n * 2)
+    assert dev.has_lut(e)
+    dev.set_lut(e, False)  # the arithmetic kernel on the same buffer
+    dev.apply(e, px, pa, n)
+    dev.set_lut(e, True)
+    want = dev.d2h(pa, n, N.U16)
+    assert got.tobytes() == want.tobytes(), f"{int(np.sum(got != want))} of {n} elements differ"
+    # and against the oracle on the 65 536 distinct inputs (exact-op chains only; transcendentals are <= 1 ulp)
+    if chain_name == "cheap8":
+        ref = orc.apply_chain(chain, dt, x[:65536].view(np.float16) if dt == N.F16 else x[:65536])
+        ref = np.asarray(ref).view(np.uint16)
+        nan = (lambda b: ((b & 0x7c00) == 0x7c00) & ((b & 0x3ff) != 0)) if dt == N.F16 else bf16_is_nan
+        assert np.all((got[:65536] == ref) | (nan(got[:65536]) & nan(ref)))
+    dev.apply(e, px, px, n)  # in place
+    assert dev.d2h(px, n, N.U16).tobytes() == want.tobytes()
+    dev.h2d(px, x)
+    dev.apply(e, px + 2, po + 2, n - 1)  # not 16-byte aligned: stays on the arithmetic (scalar) kernel, same bits
+    assert dev.d2h(po, n - 1, N.U16, offset_bytes=2).tobytes() == want[1:].tobytes()
+    for p in (px, po, pa):
+        dev.free(p)

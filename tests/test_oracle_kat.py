@@ -289,3 +289,15 @@ def test_unsupported_int_ops_are_rejected():
     # Float-bounded ops do not exist for integers in the reference (ops/unary.rs: `T: Float`)
     with pytest.raises(orc.OracleError):
         orc.apply_fn(lambda x: x.sin(), I32, [1, 2])
+
+
+def test_the_boxed_and_the_unfused_cpu_baselines_give_the_bits_of_the_fused_interpreter():
+    # src/devices/cpu/cpu_device.rs:217-229 + src/op_hint.rs:30-33 (a boxed dyn op per element per op) and
+    # src/devices/cpu_stack_ops.rs:7-15 (one loop per op): different costs, same arithmetic
+    from custos_b200.workloads import CHAIN8, CONFIG1
+    from tests.helpers import edge_values
+    x = np.concatenate([np.random.default_rng(4).uniform(-4, 4, 5000).astype(np.float32), edge_values(np.float32)])
+    for chain in (CHAIN8, CONFIG1, CHAIN8[:1]):
+        want = orc.apply_chain(chain, F32, x).view(np.uint32)
+        assert np.array_equal(orc.apply_chain_boxed(chain, x).view(np.uint32), want)
+        assert np.array_equal(orc.apply_chain_unfused(chain, x).view(np.uint32), want)
