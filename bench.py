@@ -419,6 +419,23 @@ def other_configs(local_rank: int, n: int, peak: float):
         err = np.abs(got_g.astype(np.float64) - gg.astype(np.float64))
         res["chain8_bwd_fused_f32_2^28"]["max_err_vs_oracle_sample"] = float(np.max(err / (1e-4 * np.abs(gg) + 2e-5)))
 
+    # configs[2] on f16: the same stack typed by f16 (Lazy<Mods, f16>); forward = lookup kernel, backward = one
+    # chain-grad kernel on two halves per 32-bit word (every op still rounds to binary16 like the reference)
+    with CUDA("Lazy", "Graph", "Autograd", "Base", ordinal=local_rank, dtype=np.float16) as d:
+        buf = d.new_buffer(np.float16, n).require_grad()
+        fill_tiled(d.raw, N, N.F16, buf.ptr(), n, blk_x.astype(np.float16))
+        cur = buf
+        for f, gr in zip(CHAIN8, CHAIN8_GRADS):
+            cur = d.unary_ew(cur, f, gr)
+        d.optimize_mem_graph()
+        d.unary_fusing()
+        d.set_graph_replay(True)
+        d.run()
+        cur.backward()
+        res["chain8_fwd_f16_2^28_module_stack"] = row(timeit(d.raw, d.run), n, 4)
+        res["chain8_bwd_fused_f16_2^28"] = row(timeit(d.raw, cur.backward), n, 8, launches_per_backward=1,
+                                               kernel="cb_chain_grad_vec, word path (FP32-pipe bound: 8 roundings per element)")
+
     # configs[4]: Cached+Lazy CUDA-graph replay of a 20-op sequence on 4K-element buffers (launch-latency bound)
     x4k = make_input(4096, seed=70, lo=-1, hi=1)
     rep = {}
@@ -550,7 +567,8 @@ def run_ours(args):
     # ------------------------------------------------------------ record the chain on the north-star module stack
     dev = CUDA("Lazy", "Graph", "Autograd", "Base", ordinal=local_rank)
     raw = dev.raw
-    h_in, h_out = raw.host_alloc(nbytes), raw.host_alloc(nbytes)  # pinned: the user's data lives on the host (e2e)
+    # pinned: the user's data lives on the host (e2e); CB_BENCH_WC=1 makes the input write-combined (A/B)
+    h_in, h_out = raw.host_alloc(nbytes, os.environ.get("CB_BENCH_WC") == "1"), raw.host_alloc(nbytes)
     host_in = np.ctypeslib.as_array((ctypes.c_float * n).from_address(h_in))
     host_out = np.ctypeslib.as_array((ctypes.c_float * n).from_address(h_out))
     make_input(n, seed=4 + rank, out=host_in)

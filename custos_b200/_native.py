@@ -64,6 +64,7 @@ SIGNATURES = {
     "cb_h2d": [_vp, _u64, _vp, _sz],
     "cb_d2h": [_vp, _vp, _u64, _sz],
     "cb_host_alloc": [_sz, _P(_vp)],
+    "cb_host_alloc_ex": [_sz, _u32, _P(_vp)],
     "cb_host_free": [_vp],
     "cb_h2d_async": [_vp, _u64, _vp, _sz],
     "cb_d2h_async": [_vp, _vp, _u64, _sz],

@@ -59,6 +59,7 @@ struct Tunables {
     int fuse_scale_add = 1;  // CB_FUSE_SCALE_ADD: (u * 2^k) + C and (u + C) * 2^k become one exact fma in the f32 pair path
     int h_native = 1;  // CB_H_NATIVE: f16 add / sub / mul as single HFMA2s on packed halves
     int lut16 = 1;     // CB_LUT16: f16 / bf16 unary chains on large buffers run as a shared-memory table lookup
+    int lut_shape = 0;  // CB_LUT_SHAPE (threads x units per tile x tiles per grab): 0 = 512x8x4 (default), 1 = 1024x4x8, 2 = 512x8x2, 3 = 1024x4x4, 4 = 256x16x2
     long long lut16_min_elems = 1ll << 22;  // CB_LUT16_MIN_ELEMS: shorter buffers keep the arithmetic kernel
     std::string ld_mod = ".cs";
     std::string st_mod = ".cs";

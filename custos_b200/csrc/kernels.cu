@@ -427,8 +427,6 @@ __global__ void fold_ranks_kernel(const ACC *gathered, int n_ranks, ACC *out, si
 //  * 128-bit streaming loads / stores, 8 lookups (LDS.U16) per 16-byte unit;
 //  * tiles are handed out by a device counter, so an SM that runs slower (or starts later) simply takes fewer tiles;
 //    the block that finishes last resets the counters for the next launch.
-constexpr int kLutThreads = 1024;
-constexpr int kLutUnroll = 4;
 constexpr size_t kLutBytes = 65536 * 2;
 
 __global__ void iota16_kernel(unsigned short *out)
@@ -449,31 +447,54 @@ __device__ __forceinline__ uint4 lut8(const unsigned short *lut, uint4 q)
     return make_uint4(lut2(lut, q.x), lut2(lut, q.y), lut2(lut, q.z), lut2(lut, q.w));
 }
 
+// kLutThreads threads per block (one block per SM), kLutUnroll 16-byte units per thread per tile (and as many again
+// prefetched)
+template <int kLutThreads, int kLutUnroll, int kLutGrab>
 __global__ void __launch_bounds__(kLutThreads, 1)
 lut16_kernel(const unsigned short *in, unsigned short *out, size_t n, const uint4 *table, unsigned long long *counters)
 {
     extern __shared__ uint4 lut_q[];
     for (int i = threadIdx.x; i < (int)(kLutBytes / 16); i += kLutThreads) lut_q[i] = table[i];
-    __shared__ unsigned long long next_tile;
     __syncthreads();
     const unsigned short *lut = reinterpret_cast<const unsigned short *>(lut_q);
     const size_t nunits = n / 8;
-    const size_t tile_units = (size_t)kLutThreads * kLutUnroll;
+    // Work is handed out per WARP (no block-wide barrier in the streaming loop): a warp tile is kLutUnroll rows of 32
+    // consecutive 16-byte units (512 contiguous bytes per row) and a warp takes kLutGrab consecutive tiles at a time —
+    // the first grab is static, the following ones come from a device counter (one atomic per grab: handing out
+    // single 2 KB tiles made the kernel atomic-bound at ~0.5 G atomics/s on the one address, profiles/r2_lut16_shapes.log).
+    // The loads of the NEXT tile are issued before the lookups of the current one, so global-memory latency overlaps
+    // the shared-memory work (the block-tile version was latency bound: LSU data pipe at 67 %, 16 long-scoreboard
+    // stall cycles per issue, profiles/r2_lut16_ncu.txt).
+    const size_t tile_units = (size_t)32 * kLutUnroll;
     const size_t ntiles = nunits / tile_units;
     const uint4 *pin = reinterpret_cast<const uint4 *>(in);
     uint4 *pout = reinterpret_cast<uint4 *>(out);
-    size_t tile = blockIdx.x;  // the first tile is static, the rest come from the counter
+    const unsigned int lane = threadIdx.x & 31u;
+    const size_t warps_total = (size_t)gridDim.x * (kLutThreads / 32);
+    size_t tile = ((size_t)blockIdx.x * (kLutThreads / 32) + (threadIdx.x >> 5)) * kLutGrab;
+    size_t grab_end = tile + kLutGrab;
+    uint4 cur[kLutUnroll], nxt[kLutUnroll];
+    if (tile < ntiles) {
+#pragma unroll
+        for (int u = 0; u < kLutUnroll; u++) cur[u] = ld16(pin + tile * tile_units + (size_t)u * 32 + lane);
+    }
     while (tile < ntiles) {
-        const size_t base = tile * tile_units + threadIdx.x;
-        uint4 r[kLutUnroll];
+        size_t next = tile + 1;
+        if (next == grab_end) {  // warp-uniform
+            unsigned int got = 0;  // (a 32-bit ticket: 2^32 grabs are far beyond any buffer)
+            if (lane == 0) got = atomicAdd(reinterpret_cast<unsigned int *>(&counters[0]), 1u);
+            next = ((size_t)__shfl_sync(0xffffffffu, got, 0) + warps_total) * kLutGrab;
+            grab_end = next + kLutGrab;
+        }
+        if (next < ntiles) {
 #pragma unroll
-        for (int u = 0; u < kLutUnroll; u++) r[u] = ld16(pin + base + (size_t)u * kLutThreads);
-        if (threadIdx.x == 0) next_tile = atomicAdd(&counters[0], 1ull) + gridDim.x;
+            for (int u = 0; u < kLutUnroll; u++) nxt[u] = ld16(pin + next * tile_units + (size_t)u * 32 + lane);
+        }
 #pragma unroll
-        for (int u = 0; u < kLutUnroll; u++) st16(pout + base + (size_t)u * kLutThreads, lut8(lut, r[u]));
-        __syncthreads();
-        tile = next_tile;
-        __syncthreads();
+        for (int u = 0; u < kLutUnroll; u++) st16(pout + tile * tile_units + (size_t)u * 32 + lane, lut8(lut, cur[u]));
+#pragma unroll
+        for (int u = 0; u < kLutUnroll; u++) cur[u] = nxt[u];
+        tile = next;
     }
     // ragged end: units that do not fill a tile, then the < 8 element tail
     const size_t gid = (size_t)blockIdx.x * kLutThreads + threadIdx.x;
@@ -711,21 +732,31 @@ cudaError_t launch_iota16(const LaunchCtx &ctx, void *out)
     return cudaGetLastError();
 }
 
+template <int THREADS, int UNROLL, int GRAB>
+static cudaError_t launch_lut16_t(const LaunchCtx &ctx, int sm_count, const void *in, void *out, size_t n, const void *table,
+                                  unsigned long long *counters)
+{
+    cudaError_t e = cudaFuncSetAttribute(lut16_kernel<THREADS, UNROLL, GRAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes);
+    if (e != cudaSuccess) return e;
+    const size_t block_tiles = n / 8 / ((size_t)THREADS * UNROLL);
+    int grid = sm_count;
+    if ((size_t)grid > block_tiles + 1) grid = (int)(block_tiles + 1);
+    lut16_kernel<THREADS, UNROLL, GRAB><<<grid, THREADS, kLutBytes, ctx.stream>>>((const unsigned short *)in, (unsigned short *)out, n,
+                                                                           (const uint4 *)table, counters);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_lut16(const LaunchCtx &ctx, int sm_count, const void *in, void *out, size_t n, const void *table,
-                         unsigned long long *counters)
+                         unsigned long long *counters, int shape)
 {
     (void)cudaGetLastError();
-    static bool configured = false;  // per process; the attribute is per function and context-independent for static kernels
-    cudaError_t e = cudaFuncSetAttribute(lut16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes);
-    if (e != cudaSuccess) return e;
-    configured = true;
-    (void)configured;
-    const size_t tiles = n / 8 / ((size_t)kLutThreads * kLutUnroll);
-    int grid = sm_count;
-    if ((size_t)grid > tiles + 1) grid = (int)(tiles + 1);
-    lut16_kernel<<<grid, kLutThreads, kLutBytes, ctx.stream>>>((const unsigned short *)in, (unsigned short *)out, n,
-                                                              (const uint4 *)table, counters);
-    return cudaGetLastError();
+    switch (shape) {  // CB_LUT_SHAPE: launch shapes kept for A/B measurements (profiles/r2_lut16_*.log)
+    case 1: return launch_lut16_t<1024, 4, 8>(ctx, sm_count, in, out, n, table, counters);
+    case 2: return launch_lut16_t<512, 8, 2>(ctx, sm_count, in, out, n, table, counters);
+    case 3: return launch_lut16_t<1024, 4, 4>(ctx, sm_count, in, out, n, table, counters);
+    case 4: return launch_lut16_t<256, 16, 2>(ctx, sm_count, in, out, n, table, counters);
+    default: return launch_lut16_t<512, 8, 4>(ctx, sm_count, in, out, n, table, counters);
+    }
 }
 
 cudaError_t launch_fold_ranks(const LaunchCtx &ctx, int dtype, const void *gathered, int n_ranks, void *out, size_t divisor)

@@ -45,7 +45,7 @@ cudaError_t launch_sum_exchange(const LaunchCtx &ctx, int dtype, const void *in,
 // 16-bit unary chains as a table lookup (see kernels.cu): table = 65 536 results, counters = 2 zeroed u64
 cudaError_t launch_iota16(const LaunchCtx &ctx, void *out);
 cudaError_t launch_lut16(const LaunchCtx &ctx, int sm_count, const void *in, void *out, size_t n, const void *table,
-                         unsigned long long *counters);
+                         unsigned long long *counters, int shape);
 cudaError_t launch_fold_ranks(const LaunchCtx &ctx, int dtype, const void *gathered, int n_ranks, void *out, size_t divisor);
 
 }  // namespace cb

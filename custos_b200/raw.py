@@ -139,9 +139,12 @@ class RawDevice:
         self.h2d(p, arr)
         return p
 
-    def host_alloc(self, nbytes: int) -> int:
+    def host_alloc(self, nbytes: int, write_combined: bool = False) -> int:
         p = C.c_void_p()
-        N.call("cb_host_alloc", nbytes, C.byref(p))
+        if write_combined:
+            N.call("cb_host_alloc_ex", nbytes, 1, C.byref(p))
+        else:
+            N.call("cb_host_alloc", nbytes, C.byref(p))
         return p.value
 
     def host_free(self, p: int):

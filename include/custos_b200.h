@@ -201,6 +201,10 @@ int32_t cb_h2d(cb_device *dev, uint64_t dst, const void *src, size_t bytes);
 int32_t cb_d2h(cb_device *dev, void *dst, uint64_t src, size_t bytes);
 /* pinned host memory for zero-copy-staging callers */
 int32_t cb_host_alloc(size_t bytes, void **out);
+/* CB_HOST_WRITE_COMBINED: not cached by the CPU — the host writes it at full speed, reads it very slowly, and the
+ * DMA engine reads it without snooping the CPU caches: for buffers the host only fills and the device only reads */
+#define CB_HOST_WRITE_COMBINED 1u
+int32_t cb_host_alloc_ex(size_t bytes, uint32_t flags, void **out);
 int32_t cb_host_free(void *p);
 /* asynchronous variants on the compute stream; host memory must be pinned */
 int32_t cb_h2d_async(cb_device *dev, uint64_t dst, const void *src, size_t bytes);

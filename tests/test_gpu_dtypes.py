@@ -299,3 +299,31 @@ def test_large_16bit_buffers_take_the_lookup_kernel_and_match_the_arithmetic_ker
     assert dev.d2h(po, n - 1, N.U16, offset_bytes=2).tobytes() == want[1:].tobytes()
     for p in (px, po, pa):
         dev.free(p)
+
+
+def test_narrow_unsigned_multiply_wraps_without_signed_overflow(raw_device):
+    # u16 operands are promoted to (signed) int by C++: 65535 * 65535 overflows it; the kernels multiply as unsigned int
+    dev = raw_device
+    for dt, np_t, hi in ((N.U16, np.uint16, 65535), (N.U8, np.uint8, 255)):
+        a = np.array([hi, hi, hi - 1, 2, 0, hi], np_t)
+        b = np.array([hi, 2, hi, hi, hi, 1], np_t)
+        pa, pb, po = dev.upload(a), dev.upload(b), dev.alloc(a.nbytes)
+        dev.binary(dt, N.BIN_MUL, pa, pb, po, a.size)
+        want = (a.astype(np.uint64) * b.astype(np.uint64)).astype(np_t)
+        assert dev.d2h(po, a.size, dt).tolist() == want.tolist() == orc.binary(1, dt, a, b).tolist()
+        e = dev.compile(lambda x, y: x.mul(y), dt, N.KERNEL_BINARY)
+        dev.apply2(e, pa, pb, po, a.size)
+        assert dev.d2h(po, a.size, dt).tolist() == want.tolist()
+        for p in (pa, pb, po):
+            dev.free(p)
+
+
+def test_u64_sum_wraps_unsigned_and_mean_divides_unsigned(raw_device):
+    dev = raw_device
+    x = np.full(1000, (1 << 63) // 750, np.uint64)  # the sum passes 2^63: a signed accumulator would go negative
+    p = dev.upload(x)
+    total = int(x.astype(object).sum())
+    assert (1 << 63) <= total < (1 << 64)
+    assert int(dev.sum(N.U64, p, x.size)) == total
+    assert int(dev.mean(N.U64, p, x.size)) == total // x.size
+    dev.free(p)
