@@ -419,8 +419,8 @@ def other_configs(local_rank: int, n: int, peak: float):
         err = np.abs(got_g.astype(np.float64) - gg.astype(np.float64))
         res["chain8_bwd_fused_f32_2^28"]["max_err_vs_oracle_sample"] = float(np.max(err / (1e-4 * np.abs(gg) + 2e-5)))
 
-    # configs[2] on f16: the same stack typed by f16 (Lazy<Mods, f16>); forward = lookup kernel, backward = one
-    # chain-grad kernel on two halves per 32-bit word (every op still rounds to binary16 like the reference)
+    # configs[2] on f16: the same stack typed by f16 (Lazy<Mods, f16>); forward and seeded backward are one table
+    # lookup per element each (the tables hold what the arithmetic kernels compute, a rounding after every op)
     with CUDA("Lazy", "Graph", "Autograd", "Base", ordinal=local_rank, dtype=np.float16) as d:
         buf = d.new_buffer(np.float16, n).require_grad()
         fill_tiled(d.raw, N, N.F16, buf.ptr(), n, blk_x.astype(np.float16))
@@ -434,7 +434,8 @@ def other_configs(local_rank: int, n: int, peak: float):
         cur.backward()
         res["chain8_fwd_f16_2^28_module_stack"] = row(timeit(d.raw, d.run), n, 4)
         res["chain8_bwd_fused_f16_2^28"] = row(timeit(d.raw, cur.backward), n, 8, launches_per_backward=1,
-                                               kernel="cb_chain_grad_vec, word path (FP32-pipe bound: 8 roundings per element)")
+                                               kernel="lut16_kernel<grad>: seeded with ones the backward term is a function of x alone "
+                                                      "(table filled by cb_chain_grad_vec itself)")
 
     # configs[4]: Cached+Lazy CUDA-graph replay of a 20-op sequence on 4K-element buffers (launch-latency bound)
     x4k = make_input(4096, seed=70, lo=-1, hi=1)

@@ -447,11 +447,43 @@ __device__ __forceinline__ uint4 lut8(const unsigned short *lut, uint4 q)
     return make_uint4(lut2(lut, q.x), lut2(lut, q.y), lut2(lut, q.z), lut2(lut, q.w));
 }
 
+// g + t for two packed 16-bit lanes, as the reference adds them: through f32, one round-to-nearest-even back
+// (exact for f16: an f32 holds the sum of two binary16 values exactly enough that the single rounding is the correct
+// one; bf16 is defined that way by `half`)
+template <bool BF16>
+__device__ __forceinline__ unsigned int add16x2(unsigned int g, unsigned int t)
+{
+    float g0, g1, t0, t1;
+    if (BF16) {
+        g0 = __uint_as_float(g << 16), g1 = __uint_as_float(g & 0xffff0000u);
+        t0 = __uint_as_float(t << 16), t1 = __uint_as_float(t & 0xffff0000u);
+    } else {
+        g0 = h2f((unsigned short)(g & 0xffffu)), g1 = h2f((unsigned short)(g >> 16));
+        t0 = h2f((unsigned short)(t & 0xffffu)), t1 = h2f((unsigned short)(t >> 16));
+    }
+    const float s0 = __fadd_rn(g0, t0), s1 = __fadd_rn(g1, t1);
+    unsigned int r;
+    if (BF16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(s1), "f"(s0));
+    else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(s1), "f"(s0));
+    return r;
+}
+template <bool BF16>
+__device__ __forceinline__ uint4 add16x8(uint4 g, uint4 t)
+{
+    return make_uint4(add16x2<BF16>(g.x, t.x), add16x2<BF16>(g.y, t.y), add16x2<BF16>(g.z, t.z), add16x2<BF16>(g.w, t.w));
+}
+
 // kLutThreads threads per block (one block per SM), kLutUnroll 16-byte units per thread per tile (and as many again
-// prefetched)
-template <int kLutThreads, int kLutUnroll, int kLutGrab>
+// prefetched), kLutGrab tiles per ticket.
+// MODE 0: out[i] = table[in[i]]                                  (a fused unary chain, K1/K2)
+// MODE 1 / 2 (f16 / bf16): the SEEDED backward of a fused chain — out_grad = ones makes the whole backward term a
+//   function of x alone, table[x] = (((1 * gK(x_{K-1})) ...) * g1(x)) with every 16-bit rounding of the reference:
+//   grad[i] = grad[i] + table[in[i]] (one 16-bit add, through f32 like `half`) and seed[i] = 1.
+//   4 x 2 bytes per element instead of the FP32-pipe-bound chain-grad arithmetic.
+template <int kLutThreads, int kLutUnroll, int kLutGrab, int MODE>
 __global__ void __launch_bounds__(kLutThreads, 1)
-lut16_kernel(const unsigned short *in, unsigned short *out, size_t n, const uint4 *table, unsigned long long *counters)
+lut16_kernel(const unsigned short *in, unsigned short *out, unsigned short *seed, size_t n, const uint4 *table,
+             unsigned long long *counters)
 {
     extern __shared__ uint4 lut_q[];
     for (int i = threadIdx.x; i < (int)(kLutBytes / 16); i += kLutThreads) lut_q[i] = table[i];
@@ -465,18 +497,26 @@ lut16_kernel(const unsigned short *in, unsigned short *out, size_t n, const uint
     // The loads of the NEXT tile are issued before the lookups of the current one, so global-memory latency overlaps
     // the shared-memory work (the block-tile version was latency bound: LSU data pipe at 67 %, 16 long-scoreboard
     // stall cycles per issue, profiles/r2_lut16_ncu.txt).
+    constexpr bool kGrad = MODE != 0;
+    constexpr bool kBf16 = MODE == 2;
+    constexpr unsigned int kOne = kBf16 ? 0x3f803f80u : 0x3c003c00u;
+    const uint4 ones = make_uint4(kOne, kOne, kOne, kOne);
     const size_t tile_units = (size_t)32 * kLutUnroll;
     const size_t ntiles = nunits / tile_units;
     const uint4 *pin = reinterpret_cast<const uint4 *>(in);
     uint4 *pout = reinterpret_cast<uint4 *>(out);
+    uint4 *pseed = reinterpret_cast<uint4 *>(seed);
     const unsigned int lane = threadIdx.x & 31u;
     const size_t warps_total = (size_t)gridDim.x * (kLutThreads / 32);
     size_t tile = ((size_t)blockIdx.x * (kLutThreads / 32) + (threadIdx.x >> 5)) * kLutGrab;
     size_t grab_end = tile + kLutGrab;
-    uint4 cur[kLutUnroll], nxt[kLutUnroll];
+    uint4 cur[kLutUnroll], nxt[kLutUnroll], gcur[kGrad ? kLutUnroll : 1], gnxt[kGrad ? kLutUnroll : 1];
     if (tile < ntiles) {
 #pragma unroll
-        for (int u = 0; u < kLutUnroll; u++) cur[u] = ld16(pin + tile * tile_units + (size_t)u * 32 + lane);
+        for (int u = 0; u < kLutUnroll; u++) {
+            cur[u] = ld16(pin + tile * tile_units + (size_t)u * 32 + lane);
+            if (kGrad) gcur[u] = ld16(pout + tile * tile_units + (size_t)u * 32 + lane);
+        }
     }
     while (tile < ntiles) {
         size_t next = tile + 1;
@@ -488,19 +528,47 @@ lut16_kernel(const unsigned short *in, unsigned short *out, size_t n, const uint
         }
         if (next < ntiles) {
 #pragma unroll
-            for (int u = 0; u < kLutUnroll; u++) nxt[u] = ld16(pin + next * tile_units + (size_t)u * 32 + lane);
+            for (int u = 0; u < kLutUnroll; u++) {
+                nxt[u] = ld16(pin + next * tile_units + (size_t)u * 32 + lane);
+                if (kGrad) gnxt[u] = ld16(pout + next * tile_units + (size_t)u * 32 + lane);
+            }
         }
 #pragma unroll
-        for (int u = 0; u < kLutUnroll; u++) st16(pout + tile * tile_units + (size_t)u * 32 + lane, lut8(lut, cur[u]));
+        for (int u = 0; u < kLutUnroll; u++) {
+            const size_t at = tile * tile_units + (size_t)u * 32 + lane;
+            if (kGrad) {
+                st16(pout + at, add16x8<kBf16>(gcur[u], lut8(lut, cur[u])));
+                st16(pseed + at, ones);
+            } else {
+                st16(pout + at, lut8(lut, cur[u]));
+            }
+        }
 #pragma unroll
-        for (int u = 0; u < kLutUnroll; u++) cur[u] = nxt[u];
+        for (int u = 0; u < kLutUnroll; u++) {
+            cur[u] = nxt[u];
+            if (kGrad) gcur[u] = gnxt[u];
+        }
         tile = next;
     }
     // ragged end: units that do not fill a tile, then the < 8 element tail
     const size_t gid = (size_t)blockIdx.x * kLutThreads + threadIdx.x;
     const size_t gsz = (size_t)gridDim.x * kLutThreads;
-    for (size_t u = ntiles * tile_units + gid; u < nunits; u += gsz) st16(pout + u, lut8(lut, ld16(pin + u)));
-    for (size_t i = nunits * 8 + gid; i < n; i += gsz) out[i] = lut[in[i]];
+    for (size_t u = ntiles * tile_units + gid; u < nunits; u += gsz) {
+        if (kGrad) {
+            st16(pout + u, add16x8<kBf16>(ld16(pout + u), lut8(lut, ld16(pin + u))));
+            st16(pseed + u, ones);
+        } else {
+            st16(pout + u, lut8(lut, ld16(pin + u)));
+        }
+    }
+    for (size_t i = nunits * 8 + gid; i < n; i += gsz) {
+        if (kGrad) {
+            out[i] = (unsigned short)(add16x2<kBf16>(out[i], lut[in[i]]) & 0xffffu);
+            seed[i] = (unsigned short)(kOne & 0xffffu);
+        } else {
+            out[i] = lut[in[i]];
+        }
+    }
     // the last block to get here leaves the counters at zero for the next launch
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -732,17 +800,18 @@ cudaError_t launch_iota16(const LaunchCtx &ctx, void *out)
     return cudaGetLastError();
 }
 
-template <int THREADS, int UNROLL, int GRAB>
-static cudaError_t launch_lut16_t(const LaunchCtx &ctx, int sm_count, const void *in, void *out, size_t n, const void *table,
-                                  unsigned long long *counters)
+template <int THREADS, int UNROLL, int GRAB, int MODE>
+static cudaError_t launch_lut16_t(const LaunchCtx &ctx, int sm_count, const void *in, void *out, void *seed, size_t n,
+                                  const void *table, unsigned long long *counters)
 {
-    cudaError_t e = cudaFuncSetAttribute(lut16_kernel<THREADS, UNROLL, GRAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLutBytes);
+    cudaError_t e = cudaFuncSetAttribute(lut16_kernel<THREADS, UNROLL, GRAB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kLutBytes);
     if (e != cudaSuccess) return e;
     const size_t block_tiles = n / 8 / ((size_t)THREADS * UNROLL);
     int grid = sm_count;
     if ((size_t)grid > block_tiles + 1) grid = (int)(block_tiles + 1);
-    lut16_kernel<THREADS, UNROLL, GRAB><<<grid, THREADS, kLutBytes, ctx.stream>>>((const unsigned short *)in, (unsigned short *)out, n,
-                                                                           (const uint4 *)table, counters);
+    lut16_kernel<THREADS, UNROLL, GRAB, MODE><<<grid, THREADS, kLutBytes, ctx.stream>>>(
+        (const unsigned short *)in, (unsigned short *)out, (unsigned short *)seed, n, (const uint4 *)table, counters);
     return cudaGetLastError();
 }
 
@@ -750,13 +819,21 @@ cudaError_t launch_lut16(const LaunchCtx &ctx, int sm_count, const void *in, voi
                          unsigned long long *counters, int shape)
 {
     (void)cudaGetLastError();
-    switch (shape) {  // CB_LUT_SHAPE: launch shapes kept for A/B measurements (profiles/r2_lut16_*.log)
-    case 1: return launch_lut16_t<1024, 4, 8>(ctx, sm_count, in, out, n, table, counters);
-    case 2: return launch_lut16_t<512, 8, 2>(ctx, sm_count, in, out, n, table, counters);
-    case 3: return launch_lut16_t<1024, 4, 4>(ctx, sm_count, in, out, n, table, counters);
-    case 4: return launch_lut16_t<256, 16, 2>(ctx, sm_count, in, out, n, table, counters);
-    default: return launch_lut16_t<512, 8, 4>(ctx, sm_count, in, out, n, table, counters);
+    switch (shape) {  // CB_LUT_SHAPE: launch shapes kept for A/B measurements (profiles/r2_lut16_shapes*.log)
+    case 1: return launch_lut16_t<1024, 4, 8, 0>(ctx, sm_count, in, out, nullptr, n, table, counters);
+    case 2: return launch_lut16_t<512, 8, 2, 0>(ctx, sm_count, in, out, nullptr, n, table, counters);
+    case 3: return launch_lut16_t<1024, 4, 4, 0>(ctx, sm_count, in, out, nullptr, n, table, counters);
+    case 4: return launch_lut16_t<256, 16, 2, 0>(ctx, sm_count, in, out, nullptr, n, table, counters);
+    default: return launch_lut16_t<512, 8, 4, 0>(ctx, sm_count, in, out, nullptr, n, table, counters);
     }
+}
+
+cudaError_t launch_lut16_grad_seed(const LaunchCtx &ctx, int sm_count, int dtype, const void *x, void *x_grad, void *out_grad,
+                                   size_t n, const void *table, unsigned long long *counters)
+{
+    (void)cudaGetLastError();
+    if (dtype == CB_BF16) return launch_lut16_t<512, 4, 8, 2>(ctx, sm_count, x, x_grad, out_grad, n, table, counters);
+    return launch_lut16_t<512, 4, 8, 1>(ctx, sm_count, x, x_grad, out_grad, n, table, counters);
 }
 
 cudaError_t launch_fold_ranks(const LaunchCtx &ctx, int dtype, const void *gathered, int n_ranks, void *out, size_t divisor)

@@ -46,6 +46,9 @@ cudaError_t launch_sum_exchange(const LaunchCtx &ctx, int dtype, const void *in,
 cudaError_t launch_iota16(const LaunchCtx &ctx, void *out);
 cudaError_t launch_lut16(const LaunchCtx &ctx, int sm_count, const void *in, void *out, size_t n, const void *table,
                          unsigned long long *counters, int shape);
+// seeded backward of a 16-bit chain: x_grad[i] += table[x[i]], out_grad[i] = 1 (dtype CB_F16 or CB_BF16)
+cudaError_t launch_lut16_grad_seed(const LaunchCtx &ctx, int sm_count, int dtype, const void *x, void *x_grad, void *out_grad,
+                                   size_t n, const void *table, unsigned long long *counters);
 cudaError_t launch_fold_ranks(const LaunchCtx &ctx, int dtype, const void *gathered, int n_ranks, void *out, size_t divisor);
 
 }  // namespace cb

@@ -327,3 +327,45 @@ def test_u64_sum_wraps_unsigned_and_mean_divides_unsigned(raw_device):
     assert int(dev.sum(N.U64, p, x.size)) == total
     assert int(dev.mean(N.U64, p, x.size)) == total // x.size
     dev.free(p)
+
+
+@pytest.mark.parametrize("dt", [N.F16, N.BF16])
+@pytest.mark.parametrize("kind", ["chain_grad", "unary_grad"])
+def test_seeded_16bit_backward_by_lookup_matches_the_arithmetic_kernel(raw_device, dt, kind):
+    """`backward()` seeds out_grad with ones; the backward term of a 16-bit expression is then a function of lhs alone
+    and large buffers take lut16_kernel<MODE 1 / 2>: lhs_grad += table[lhs], out_grad = 1.  Same bits as the arithmetic
+    kernel for every input pattern and every start value of the gradient, signed zeros included."""
+    from custos_b200.workloads import CHAIN8_GRADS
+    dev = raw_device
+    if kind == "chain_grad":
+        e = dev.compile(CHAIN8 + CHAIN8_GRADS, dt, N.KERNEL_CHAIN_GRAD)
+    else:
+        e = dev.compile(lambda v: v.cos().mul(0.5), dt, N.KERNEL_UNARY_GRAD)
+    assert dev.has_lut(e)
+    n = (1 << 22) + 8 * 512 * 5 + 3
+    rng = np.random.default_rng(33)
+    x = np.concatenate([np.arange(65536, dtype=np.uint16), rng.integers(0, 65536, n - 65536).astype(np.uint16)])
+    one = 0x3c00 if dt == N.F16 else 0x3f80
+    g0 = rng.integers(0, 65536, n).astype(np.uint16)
+    g0[:65536:3] = 0x8000  # -0 start values: a -0 term must survive
+    g0[1:65536:3] = 0x0000
+    px, pg, po = dev.upload(x), dev.upload(g0), dev.alloc(n * 2)
+    before = dev.launches
+    dev.unary_grad_ex(e, px, pg, po, n, N.GRAD_SEED_ONES)  # lookup kernel
+    assert dev.launches - before == 1
+    got_g, got_o = dev.d2h(pg, n, N.U16), dev.d2h(po, n, N.U16)
+    dev.h2d(pg, g0)
+    dev.clear(N.U16, po, n)
+    dev.set_lut(e, False)
+    dev.unary_grad_ex(e, px, pg, po, n, N.GRAD_SEED_ONES)  # arithmetic kernel
+    dev.set_lut(e, True)
+    want_g, want_o = dev.d2h(pg, n, N.U16), dev.d2h(po, n, N.U16)
+    assert np.all(want_o == one) and np.all(got_o == one)
+    assert got_g.tobytes() == want_g.tobytes(), f"{int(np.sum(got_g != want_g))} of {n} gradients differ"
+    # unseeded calls never take the table
+    dev.h2d(pg, g0)
+    dev.fill(dt, po, n, 1.0)
+    dev.unary_grad_ex(e, px, pg, po, n, 0)
+    assert dev.d2h(pg, n, N.U16).tobytes() == want_g.tobytes()
+    for p in (px, pg, po):
+        dev.free(p)
