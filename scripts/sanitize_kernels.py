@@ -10,10 +10,13 @@ kernels (binary, fill, copy, two-pass sum), unaligned sub-slices, in-place appli
 the host pipeline (cb_apply_host) and the module stack (Lazy + Graph fusing, Autograd backward).
 Exits non-zero on a wrong result; the sanitizer reports memory errors itself.
 """
+import os
 import sys
 from pathlib import Path
 
 import numpy as np
+
+os.environ.setdefault("CB_LUT16_MIN_ELEMS", "2048")  # let small buffers take the table-lookup kernels too
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
@@ -56,6 +59,18 @@ def main():
             g = dev.compile((lambda v: v.mul(2.0).cos()) if isf else (lambda v: v.mul(2)), dt, N.KERNEL_UNARY_GRAD)
             dev.unary_grad(g, py, po, px, n)
             dev.unary_grad(g, py + sz, po + sz, px + sz, n)
+            dev.unary_grad_ex(g, py, po, px, n, N.GRAD_SEED_ONES)   # seed written by the kernel (lookup kernel for large 16-bit n)
+            # the backward of a whole chain in one kernel
+            fw = (CHAIN8 if n > 1000 else CHEAP8) if isf else [lambda v: v.mul(3).add(1), lambda v: v.sub(2)]
+            gr = (CHAIN8_GRADS if n > 1000 else [lambda v: 1.0] * 8) if isf else [lambda v: 3, lambda v: 1]
+            cg = dev.compile(list(fw) + list(gr), dt, N.KERNEL_CHAIN_GRAD)
+            dev.unary_grad_ex(cg, py, po, px, n, 0)
+            dev.unary_grad_ex(cg, py, po, px, n, N.GRAD_SEED_ONES)
+            dev.unary_grad_ex(cg, py + sz, po + sz, px + sz, n, N.GRAD_SEED_ONES)
+            if dt in (N.F16, N.BF16):
+                dev.set_lut(e, False)
+                dev.apply(e, py, po, n)                   # the arithmetic kernel where the lookup kernel ran above
+                dev.set_lut(e, True)
             b2 = dev.compile((lambda a, b: a.mul(b).max(0.5)) if isf else (lambda a, b: a.mul(b).add(a)), dt, N.KERNEL_BINARY)
             dev.apply2(b2, px, py, po, n)
             dev.apply2(b2, px + sz, py + sz, po + sz, n)
@@ -111,6 +126,21 @@ def main():
         d.unary_fusing()
         d.run()
         assert np.isfinite(cur.replace().read()).all()
+    for dt, xs in ((np.float32, x), (np.float16, x.astype(np.float16))):  # fused forward + fused (f16: looked-up) backward
+        with CUDA("Lazy", "Graph", "Autograd", "Base", dtype=dt) as d:
+            buf = d.buffer(xs).require_grad()
+            cur = buf
+            for f, g in zip(CHAIN8, CHAIN8_GRADS):
+                cur = d.unary_ew(cur, f, g)
+            d.optimize_mem_graph()
+            d.unary_fusing()
+            d.set_graph_replay(True)
+            for _ in range(2):
+                d.run()
+                cur.backward()
+            assert np.isfinite(buf.grad().read().astype(np.float32)).all()
+            d.zero_grad()
+            assert d.sum(cur.replace()) == d.sum(cur.replace())
     with CUDA("Autograd", "Cached", "Base") as d:
         buf = d.buffer(x).require_grad()
         cur = buf
