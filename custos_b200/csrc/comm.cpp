@@ -262,7 +262,7 @@ static int32_t comm_reduce(cb_comm *c, int32_t dtype, uint64_t in, size_t n_loca
         x.status = c->status_dev;
         if (n_local && !in) return fail(CB_ERR_INVALID_ARG, "null buffer");
         cudaError_t e = cb::launch_sum_exchange(dev->ctx(), dtype, reinterpret_cast<const void *>(in), n_local, dev->sum_partials,
-                                                dev->sum_ticket, reinterpret_cast<void *>(out), divisor, x);
+                                                dev->sum_ticket, reinterpret_cast<void *>(out), divisor, x, dev->next_sum_pdl(in, n_local * cb::dtype_size(dtype), out));
         if (e != cudaSuccess) return dev->cuda_fail(e, "sum + exchange kernel");
         dev->launches += 1;  // reduce, fold and exchange are one launch
         return CB_OK;

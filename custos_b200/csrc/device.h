@@ -58,6 +58,7 @@ struct Tunables {
     int neg_xor = 0;    // CB_NEG_XOR=1: f32 pair neg flips the sign bits on the integer pipe (no gain measured)
     int fuse_scale_add = 1;  // CB_FUSE_SCALE_ADD: (u * 2^k) + C and (u + C) * 2^k become one exact fma in the f32 pair path
     int h_native = 1;  // CB_H_NATIVE: f16 add / sub / mul as single HFMA2s on packed halves
+    int sum_pdl = 1;   // CB_SUM_PDL: consecutive sums overlap through programmatic dependent launch
     int lut16 = 1;     // CB_LUT16: f16 / bf16 unary chains on large buffers run as a shared-memory table lookup
     int lut_shape = 0;  // CB_LUT_SHAPE (threads x units per tile x tiles per grab): 0 = 512x8x4 (default), 1 = 1024x4x8, 2 = 512x8x2, 3 = 1024x4x4, 4 = 256x16x2
     long long lut16_min_elems = 1ll << 22;  // CB_LUT16_MIN_ELEMS: shorter buffers keep the arithmetic kernel
@@ -127,7 +128,14 @@ struct cb_device {
     // reduction scratch
     void *sum_partials = nullptr;  // kSumMaxBlocks x 8 bytes
     unsigned long long *lut_counters = nullptr;  // tile / finished-block counters of lut16_kernel, zero between launches
-    unsigned int *sum_ticket = nullptr;  // device counter of the one-launch sum (last block folds); zero between launches
+    unsigned int *sum_ticket = nullptr;  // two device counters of the one-launch sum (last block folds); zero between launches
+    // programmatic dependent launch of back-to-back sums: every entry point that enqueues work bumps op_seq in use();
+    // a sum may start under the tail of the previous kernel only if that kernel was the previous sum
+    mutable uint64_t op_seq = 0;
+    uint64_t sum_seq_mark = ~0ull;
+    uint64_t sum_calls = 0;
+    uint64_t last_sum_out = 0;  // where the previous sum writes its scalar: a sum that READS it must wait for it
+    cb::SumPdl next_sum_pdl(uint64_t in, size_t in_bytes, uint64_t out);
     void *sum_scalar = nullptr;    // 8 bytes device
     void *sum_host = nullptr;      // 8 bytes pinned
 

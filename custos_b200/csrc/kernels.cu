@@ -304,9 +304,16 @@ __device__ __forceinline__ ACC ld_partial(const ACC *p)
 // divisor > 0: mean = sum / (ACC)divisor, one IEEE division (integers: truncating)
 template <typename T, typename ACC, bool ALIGNED, int UNROLL, bool XCHG>
 __global__ void __launch_bounds__(kThreads)
-sum_kernel(const T *in, size_t n, size_t chunk, ACC *partials, unsigned int *ticket, ACC *out, size_t divisor, XchgArgs x)
+sum_kernel(const T *in, size_t n, size_t chunk, ACC *partials, unsigned int *ticket, ACC *out, size_t divisor, XchgArgs x,
+           unsigned int pdl)
 {
     constexpr int VEC = 16 / sizeof(T);
+    // Programmatic dependent launch (the kernel is launched with programmatic stream serialisation): when the kernel
+    // before this one on the stream is ANOTHER sum (pdl bit 0; the host alternates two sets of partials / tickets, and the
+    // exchange slots alternate by call parity anyway) the streaming pass below may start while that sum's last block is
+    // still folding and waiting for its peers — the SMs would otherwise idle through every exchange round trip.  After
+    // anything else the blocks wait for the preceding kernel first, exactly like a plain launch.
+    if (!(pdl & 1u)) asm volatile("griddepcontrol.wait;" ::: "memory");
     const size_t begin = (size_t)blockIdx.x * chunk;
     ACC acc[VEC];
 #pragma unroll
@@ -354,9 +361,16 @@ sum_kernel(const T *in, size_t n, size_t chunk, ACC *partials, unsigned int *tic
         is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (!is_last) return;
+    if (!is_last) {
+        asm volatile("griddepcontrol.launch_dependents;");  // this block is done with everything a following sum shares
+        return;
+    }
+    // the last block first makes sure the preceding sum is complete (its `out`, its ticket reset), then lets the next
+    // one start streaming under this call's fold + exchange
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     __threadfence();
-    if (threadIdx.x == 0) *ticket = 0u;  // ready for the next launch (launches on one device are stream ordered)
+    if (threadIdx.x == 0) *ticket = 0u;  // ready for the launch after next (which uses this set again)
 
     // pass 2: thread t folds partials t, t + 256, ... then the same tree
     ACC t = (ACC)0;
@@ -619,37 +633,47 @@ cudaError_t launch_binary_op(const LaunchCtx &ctx, int op, const void *lhs, cons
 
 template <typename T, typename ACC, bool XCHG>
 cudaError_t launch_sum_t(const LaunchCtx &ctx, const void *in, size_t n, int blocks, size_t chunk, void *partials,
-                         unsigned int *ticket, void *out, size_t divisor, const XchgArgs &x)
+                         unsigned int *ticket, void *out, size_t divisor, const XchgArgs &x, const SumPdl &pdl)
 {
     // n == 0 (an empty slice of a sharded buffer): one block, nothing to read, the partial is 0 — the rank still takes
     // part in the exchange
     if (n == 0) blocks = 1;
-    if (aligned16(in))
-        sum_kernel<T, ACC, true, 4, XCHG><<<blocks, kThreads, 0, ctx.stream>>>((const T *)in, n, chunk ? chunk : 1, (ACC *)partials,
-                                                                              ticket, (ACC *)out, divisor, x);
-    else
-        sum_kernel<T, ACC, false, 1, XCHG><<<blocks, kThreads, 0, ctx.stream>>>((const T *)in, n, chunk ? chunk : 1, (ACC *)partials,
-                                                                               ticket, (ACC *)out, divisor, x);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = ctx.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl.enabled ? 1 : 0;
+    // the two parities own separate partials and tickets
+    ACC *parts = (ACC *)partials + (pdl.parity ? kSumMaxBlocks : 0);
+    unsigned int *tick = ticket + (pdl.parity ? 1 : 0);
+    const unsigned int flags = (pdl.enabled && pdl.after_sum) ? 1u : 0u;
+    const size_t ch = chunk ? chunk : 1;
+    if (aligned16(in)) return cudaLaunchKernelEx(&cfg, sum_kernel<T, ACC, true, 4, XCHG>, (const T *)in, n, ch, parts, tick, (ACC *)out, divisor, x, flags);
+    return cudaLaunchKernelEx(&cfg, sum_kernel<T, ACC, false, 1, XCHG>, (const T *)in, n, ch, parts, tick, (ACC *)out, divisor, x, flags);
 }
 
 template <bool XCHG>
 cudaError_t launch_sum_dtype(const LaunchCtx &ctx, int dtype, const void *in, size_t n, int blocks, size_t chunk, void *partials,
-                             unsigned int *ticket, void *out, size_t divisor, const XchgArgs &x)
+                             unsigned int *ticket, void *out, size_t divisor, const XchgArgs &x, const SumPdl &pdl)
 {
     switch (dtype) {
-    case CB_F32: return launch_sum_t<float, float, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
-    case CB_F64: return launch_sum_t<double, double, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
-    case CB_F16: return launch_sum_t<half_bits, float, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
-    case CB_I32: return launch_sum_t<int, long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
-    case CB_I64: return launch_sum_t<long long, long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
-    case CB_U32: return launch_sum_t<unsigned int, long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
-    case CB_U8: return launch_sum_t<unsigned char, long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
-    case CB_BF16: return launch_sum_t<bf16_bits, float, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
-    case CB_I8: return launch_sum_t<signed char, long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
-    case CB_I16: return launch_sum_t<short, long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
-    case CB_U16: return launch_sum_t<unsigned short, long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
-    case CB_U64: return launch_sum_t<unsigned long long, unsigned long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x);
+    case CB_F32: return launch_sum_t<float, float, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x, pdl);
+    case CB_F64: return launch_sum_t<double, double, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x, pdl);
+    case CB_F16: return launch_sum_t<half_bits, float, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x, pdl);
+    case CB_I32: return launch_sum_t<int, long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x, pdl);
+    case CB_I64: return launch_sum_t<long long, long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x, pdl);
+    case CB_U32: return launch_sum_t<unsigned int, long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x, pdl);
+    case CB_U8: return launch_sum_t<unsigned char, long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x, pdl);
+    case CB_BF16: return launch_sum_t<bf16_bits, float, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x, pdl);
+    case CB_I8: return launch_sum_t<signed char, long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x, pdl);
+    case CB_I16: return launch_sum_t<short, long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x, pdl);
+    case CB_U16: return launch_sum_t<unsigned short, long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x, pdl);
+    case CB_U64: return launch_sum_t<unsigned long long, unsigned long long, XCHG>(ctx, in, n, blocks, chunk, partials, ticket, out, divisor, x, pdl);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -772,7 +796,7 @@ void sum_plan(int dtype, size_t n, int *blocks, size_t *chunk, int *threads, int
 }
 
 cudaError_t launch_sum(const LaunchCtx &ctx, int dtype, const void *in, size_t n, void *partials, unsigned int *ticket,
-                       void *out, size_t divisor)
+                       void *out, size_t divisor, const SumPdl &pdl)
 {
     (void)cudaGetLastError();  // a stale error of an earlier, unchecked call must not be blamed on this launch
     int blocks, threads, vec, threads2;
@@ -780,17 +804,17 @@ cudaError_t launch_sum(const LaunchCtx &ctx, int dtype, const void *in, size_t n
     sum_plan(dtype, n, &blocks, &chunk, &threads, &vec, &threads2);
     XchgArgs none;
     memset(&none, 0, sizeof none);
-    return launch_sum_dtype<false>(ctx, dtype, in, n, blocks, chunk, partials, ticket, out, divisor, none);
+    return launch_sum_dtype<false>(ctx, dtype, in, n, blocks, chunk, partials, ticket, out, divisor, none, pdl);
 }
 
 cudaError_t launch_sum_exchange(const LaunchCtx &ctx, int dtype, const void *in, size_t n, void *partials, unsigned int *ticket,
-                                void *out, size_t divisor, const XchgArgs &x)
+                                void *out, size_t divisor, const XchgArgs &x, const SumPdl &pdl)
 {
     (void)cudaGetLastError();
     int blocks = 1, threads, vec, threads2;
     size_t chunk = 0;
     if (n) sum_plan(dtype, n, &blocks, &chunk, &threads, &vec, &threads2);
-    return launch_sum_dtype<true>(ctx, dtype, in, n, blocks, chunk, partials, ticket, out, divisor, x);
+    return launch_sum_dtype<true>(ctx, dtype, in, n, blocks, chunk, partials, ticket, out, divisor, x, pdl);
 }
 
 cudaError_t launch_iota16(const LaunchCtx &ctx, void *out)

@@ -24,9 +24,16 @@ cudaError_t launch_copy(const LaunchCtx &ctx, void *dst, const void *src, size_t
 int launch_copy_count(const void *dst, const void *src, size_t bytes);
 void sum_plan(int dtype, size_t n, int *blocks, size_t *chunk, int *threads, int *vec, int *threads2);
 // partials: device scratch of kSumMaxBlocks accumulators; out: device scalar of the accumulation type
-// (`ticket`: a zero-initialised device counter owned by the device; the kernel leaves it at zero)
+// Programmatic dependent launch of consecutive sums (see sum_kernel): `parity` selects one of the two sets of partials
+// / tickets, `after_sum` says that the kernel before this one on the stream is a sum of the other parity.
+struct SumPdl {
+    bool enabled;
+    bool after_sum;
+    int parity;
+};
+// (`partials`: 2 x kSumMaxBlocks accumulators; `ticket`: two zero-initialised device counters owned by the device, left at zero)
 cudaError_t launch_sum(const LaunchCtx &ctx, int dtype, const void *in, size_t n, void *partials, unsigned int *ticket, void *out,
-                       size_t divisor);
+                       size_t divisor, const SumPdl &pdl);
 // cross-GPU exchange of reduction totals through peer-mapped memory (see kernels.cu)
 constexpr int kMaxRanks = 64;
 struct XchgSlot {
@@ -41,7 +48,7 @@ struct XchgArgs {
     int *status;  // host-mapped flag: the kernel stores the call number here when a peer never arrived
 };
 cudaError_t launch_sum_exchange(const LaunchCtx &ctx, int dtype, const void *in, size_t n, void *partials, unsigned int *ticket,
-                                void *out, size_t divisor, const XchgArgs &x);
+                                void *out, size_t divisor, const XchgArgs &x, const SumPdl &pdl);
 // 16-bit unary chains as a table lookup (see kernels.cu): table = 65 536 results, counters = 2 zeroed u64
 cudaError_t launch_iota16(const LaunchCtx &ctx, void *out);
 cudaError_t launch_lut16(const LaunchCtx &ctx, int sm_count, const void *in, void *out, size_t n, const void *table,

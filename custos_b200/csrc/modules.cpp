@@ -416,6 +416,30 @@ void free_replay(cbm_device *d)
 }
 
 
+// Recorded operations that READ buffer `id` (every argument an op does not write).  Ops added through
+// cbm_binary_into / cbm_add_unary_grad / cbm_clear_op never went through retrieve(), so the graph has no edge for them:
+// the fusing and aliasing passes count them here before they stop writing, or overwrite, a buffer.
+size_t readers_of(const cbm_device *d, uint64_t id)
+{
+    size_t n = 0;
+    for (const Op &o : d->ops) {
+        if (o.kind == OpKind::NoOp) continue;
+        for (size_t a = 0; a < o.arg_ids.size(); a++) {
+            if (o.arg_ids[a] != id) continue;
+            bool writes = false;
+            switch (o.kind) {
+            case OpKind::Apply: writes = a == 0; break;                 // (out, in)
+            case OpKind::UnaryGrad: writes = false; break;              // lhs_grad is read-modify-write: counts as a reader
+            case OpKind::Binary: case OpKind::Apply2: writes = a == 2; break;  // (lhs, rhs, out)
+            case OpKind::Clear: writes = true; break;
+            default: break;
+            }
+            if (!writes) n++;
+        }
+    }
+    return n;
+}
+
 // What a pass that destroys the intermediates x_1 .. x_{K-1} of a unary chain ids = [x_0, x_1, .., x_K] (unary
 // fusing: never written; memory-graph aliasing: overwritten) has to know about the Autograd tape.
 enum class TapePlan { NoTape, Fused, Blocked };
@@ -1114,6 +1138,15 @@ extern "C" int32_t cbm_optimize_mem_graph(cbm_device *d)
             auto def = by_id.find(head->second);
             if (def == by_id.end()) continue;  // allocated earlier: nothing to share any more
             const Deferred a = def->second;
+            {
+                // every member but the last is overwritten by its successor: it may have that one reader only
+                bool extra_reader = readers_of(d, head->second) > 1;
+                for (size_t m = 0; m + 1 < t.use_cache_idxs.size() && !extra_reader; m++) {
+                    auto uid = d->idx_to_buf_id.find(t.use_cache_idxs[m]);
+                    extra_reader = uid != d->idx_to_buf_id.end() && readers_of(d, uid->second) > 1;
+                }
+                if (extra_reader) continue;
+            }
             if (d->has(CBM_AUTOGRAD) && !d->tape.empty()) {
                 // sharing one allocation overwrites every buffer of the trace but the last; grad functions that read
                 // them must become one recomputing chain-grad kernel first, else the trace keeps its own buffers
@@ -1220,8 +1253,12 @@ extern "C" int32_t cbm_unary_fusing(cbm_device *d)
                 if (op_idx[k] < 0) return false;
                 const Op &o = d->ops[(size_t)op_idx[k]];
                 if (!(o.kind == OpKind::Apply && o.unary_hint) || o.dtype != dtype) return false;
-                // the op must consume what the previous op of the run produced
-                return k == prev_k || o.arg_ids[1] == d->ops[(size_t)op_idx[prev_k]].arg_ids[0];
+                if (k == prev_k) return true;
+                // the op must consume what the previous op of the run produced, and be its ONLY reader: an op recorded
+                // with a caller-owned output (cbm_binary_into, a recorded add_unary_grad) reads buffers the graph knows
+                // nothing about, and fusing the producer away would feed it zeros
+                const uint64_t mid = d->ops[(size_t)op_idx[prev_k]].arg_ids[0];
+                return o.arg_ids[1] == mid && readers_of(d, mid) == 1;
             };
             if (op_idx[i] < 0 || !(d->ops[(size_t)op_idx[i]].kind == OpKind::Apply && d->ops[(size_t)op_idx[i]].unary_hint)) {
                 i++;

@@ -551,3 +551,41 @@ def test_apply_host_pipelined_and_pageable(raw_device):
     out = np.zeros(n, np.float32)
     dev.apply_host(e, x.ctypes.data, out.ctypes.data, n)
     assert_bit_exact(out, want, "cb_apply_host (pageable)")
+
+
+def test_back_to_back_sums_overlap_without_losing_a_dependency(raw_device):
+    """Consecutive sums are launched with programmatic stream serialisation: the streaming pass of a sum may start while
+    the previous sum's last block is still folding.  Results must not change — also when a sum READS the scalar the
+    previous one writes (row sums into a buffer, then the sum of that buffer), and when other kernels sit in between."""
+    dev = raw_device
+    rows, n = 64, 70_001
+    rng = np.random.default_rng(77)
+    data = rng.uniform(-1, 1, (rows, n)).astype(np.float32)
+    p = dev.upload(data.reshape(-1))
+    sums = dev.alloc(rows * 4)
+    total = dev.alloc(64)
+    plan = sum_plan(N.F32, n)
+    want_rows = np.array([orc.sum_two_pass(orc.F32, data[r], plan["blocks"], plan["chunk"], plan["threads"], plan["vec"],
+                                           plan["threads2"]) for r in range(rows)], np.float32)
+    plan2 = sum_plan(N.F32, rows)
+    want_total = orc.sum_two_pass(orc.F32, want_rows, plan2["blocks"], plan2["chunk"], plan2["threads"], plan2["vec"], plan2["threads2"])
+    for rep in range(20):
+        dev.clear(N.F32, sums, rows)
+        for r in range(rows):  # 64 sums back to back, each into its own slot
+            dev.sum_into(N.F32, p + 4 * r * n, n, sums + 4 * r)
+        dev.sum_into(N.F32, sums, rows, total)  # reads what the sum just before it wrote
+        got_rows, got_total = dev.d2h(sums, rows, N.F32), dev.d2h(total, 1, N.F32)[0]
+        assert got_rows.tobytes() == want_rows.tobytes(), rep
+        assert got_total.tobytes() == want_total.tobytes(), rep
+    # a producer kernel between two sums: the second sum must see its output
+    e = dev.compile(lambda v: v.mul(2.0), N.F32)
+    q = dev.alloc(n * 4)
+    for rep in range(10):
+        dev.sum_into(N.F32, p, n, total)
+        dev.apply(e, p + 4 * n * (rep % rows), q, n)
+        dev.sum_into(N.F32, q, n, total)
+        want = orc.sum_two_pass(orc.F32, (data[rep % rows] * np.float32(2)), plan["blocks"], plan["chunk"], plan["threads"], plan["vec"],
+                                plan["threads2"])
+        assert dev.d2h(total, 1, N.F32)[0].tobytes() == want.tobytes(), rep
+    for ptr in (p, sums, total, q):
+        dev.free(ptr)

@@ -811,3 +811,24 @@ def test_autograd_state_does_not_survive_the_buffer():
             assert b.grad().read().tolist() == [0.] * 4
             b.drop()
         assert seen, "the pool never recycled an address: the test did not exercise the case"
+
+
+def test_fusing_and_aliasing_respect_readers_the_graph_does_not_know():
+    # cbm_binary_into records an op with a caller-owned output: no retrieve(), hence no graph edge (the reference's
+    # tests do this with their own kernels, src/devices/cuda/lazy.rs:96-141).  x1 is read by it AND by the next unary
+    # op: fusing x1 away, or letting x2 overwrite it, would hand the binary op the wrong operand.
+    n = 3000
+    x = random_inputs(N.F32, n, 21, -2, 2)
+    for prepare in (lambda d: d.unary_fusing(), lambda d: d.optimize_mem_graph(), lambda d: (d.optimize_mem_graph(), d.unary_fusing())):
+        with CUDA("Lazy", "Graph", "Base") as dev:
+            buf = dev.buffer(x)
+            side = dev.new_buffer(np.float32, n)
+            x1 = dev.apply_fn(buf, lambda v: v.mul(2.0))
+            x2 = dev.apply_fn(x1, lambda v: v.add(1.0))
+            x3 = dev.apply_fn(x2, lambda v: v.neg())
+            dev.add_into(x1, buf, side)  # side = x1 + x, recorded AFTER the ops that could clobber x1
+            prepare(dev)
+            dev.run()
+            a1 = orc.apply_fn(lambda v: v.mul(2.0), orc.F32, x)
+            assert_bit_exact(side.read(), orc.binary(0, orc.F32, a1, x), "the caller-owned binary op saw the real x1")
+            assert_bit_exact(x3.replace().read(), orc.apply_chain([lambda v: v.mul(2.0), lambda v: v.add(1.0), lambda v: v.neg()], orc.F32, x), "chain")
