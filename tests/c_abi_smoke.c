@@ -70,6 +70,52 @@ int main(void)
     printf("sum = %.6f (fp64 reference %.6f)\n", s, truth);
     if (fabs((double)s - truth) > 1e-6 * 3.0e5) return 1;
 
+    /* ---- the north-star stack from C: CUDA<Lazy<Graph<Autograd<Base>>>>, three unary_ew ops (x * 2, sin, + 1),
+     * unary_fusing, run() and backward(): ONE forward kernel and ONE recomputing backward kernel ---------------- */
+    {
+        cbm_device *md = NULL;
+        CHECK(cbm_device_create(0, CBM_LAZY | CBM_GRAPH | CBM_AUTOGRAD, CB_F32, &md));
+        cbm_buf bx = 0, b1 = 0, b2 = 0, b3 = 0, bg = 0;
+        CHECK(cbm_buffer_from_host(md, CB_F32, x, N, &bx));
+        CHECK(cbm_buffer_require_grad(md, bx));
+        const cb_node f_mul2[3] = {{CB_OP_X, -1, -1, 0, 0.0, 0}, {CB_OP_CONST, -1, -1, 0, 2.0, 0}, {CB_OP_MUL, 0, 1, 0, 0.0, 0}};
+        const cb_node g_two[1] = {{CB_OP_CONST, -1, -1, 0, 2.0, 0}};
+        const cb_node f_sin[2] = {{CB_OP_X, -1, -1, 0, 0.0, 0}, {CB_OP_SIN, 0, -1, 0, 0.0, 0}};
+        const cb_node g_cos[2] = {{CB_OP_X, -1, -1, 0, 0.0, 0}, {CB_OP_COS, 0, -1, 0, 0.0, 0}};
+        const cb_node f_add1[3] = {{CB_OP_X, -1, -1, 0, 0.0, 0}, {CB_OP_CONST, -1, -1, 0, 1.0, 0}, {CB_OP_ADD, 0, 1, 0, 0.0, 0}};
+        const cb_node g_one[1] = {{CB_OP_CONST, -1, -1, 0, 1.0, 0}};
+        CHECK(cbm_unary_ew(md, bx, f_mul2, 3, g_two, 1, &b1));
+        CHECK(cbm_unary_ew(md, b1, f_sin, 2, g_cos, 2, &b2));
+        CHECK(cbm_unary_ew(md, b2, f_add1, 3, g_one, 1, &b3));
+        CHECK(cbm_optimize_mem_graph(md));
+        CHECK(cbm_unary_fusing(md));
+        CHECK(cbm_run(md));
+        CHECK(cbm_backward(md, b3));
+        cb_device *raw = NULL;
+        CHECK(cbm_device_raw(md, &raw));
+        uint64_t before = 0, after = 0;
+        CHECK(cb_launch_count(raw, &before));
+        CHECK(cbm_run(md));
+        CHECK(cbm_backward(md, b3));
+        CHECK(cb_launch_count(raw, &after));
+        printf("fused forward + backward: %llu kernels\n", (unsigned long long)(after - before));
+        if (after - before != 2) return 1;
+        CHECK(cbm_buffer_read(md, b3, y, N));
+        CHECK(cbm_grad(md, bx, &bg));
+        CHECK(cbm_buffer_read(md, bg, z, N));
+        double worst_y = 0.0, worst_g = 0.0;
+        for (int i = 0; i < N; i++) {
+            const float t = x[i] * 2.0f;
+            const double dy_ = fabs((double)y[i] - (double)(sinf(t) + 1.0f));
+            const double dg = fabs((double)z[i] / 2.0 - (double)(cosf(t) * 2.0f)); /* two backward passes accumulated */
+            if (dy_ > worst_y) worst_y = dy_;
+            if (dg > worst_g) worst_g = dg;
+        }
+        printf("module stack: max |y - libm| = %.3e, max |grad - libm| = %.3e\n", worst_y, worst_g);
+        if (worst_y > 5e-7 || worst_g > 1e-6) return 1;
+        CHECK(cbm_device_destroy(md));
+    }
+
     uint64_t launches = 0;
     CHECK(cb_launch_count(dev, &launches));
     printf("kernels launched: %llu\n", (unsigned long long)launches);
