@@ -58,6 +58,7 @@ struct Tunables {
     int neg_xor = 0;    // CB_NEG_XOR=1: f32 pair neg flips the sign bits on the integer pipe (no gain measured)
     int fuse_scale_add = 1;  // CB_FUSE_SCALE_ADD: (u * 2^k) + C and (u + C) * 2^k become one exact fma in the f32 pair path
     int h_native = 1;  // CB_H_NATIVE: f16 add / sub / mul as single HFMA2s on packed halves
+    int pdl = 1;       // CB_PDL: expression and binary kernels are launched with programmatic stream serialisation
     int sum_pdl = 1;   // CB_SUM_PDL: consecutive sums overlap through programmatic dependent launch
     int lut16 = 1;     // CB_LUT16: f16 / bf16 unary chains on large buffers run as a shared-memory table lookup
     int lut_shape = 0;  // CB_LUT_SHAPE (threads x units per tile x tiles per grab): 0 = 512x8x4 (default), 1 = 1024x4x8, 2 = 512x8x2, 3 = 1024x4x4, 4 = 256x16x2
@@ -77,6 +78,7 @@ struct DriverApi {
     CUresult (*ModuleGetFunction)(CUfunction *, CUmodule, const char *) = nullptr;
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                              CUstream, void **, void **) = nullptr;
+    CUresult (*LaunchKernelEx)(const CUlaunchConfig *, CUfunction, void **, void **) = nullptr;  // optional
     CUresult (*GetErrorString)(CUresult, const char **) = nullptr;
     CUresult (*OccupancyMaxActiveBlocks)(int *, CUfunction, int, size_t) = nullptr;
     bool loaded = false;
@@ -139,7 +141,10 @@ struct cb_device {
     void *sum_scalar = nullptr;    // 8 bytes device
     void *sum_host = nullptr;      // 8 bytes pinned
 
-    cb::LaunchCtx ctx() const { return cb::LaunchCtx{stream, sm_count * cb::tunables().blocks_per_sm * cb::tunables().waves}; }
+    cb::LaunchCtx ctx() const
+    {
+        return cb::LaunchCtx{stream, sm_count * cb::tunables().blocks_per_sm * cb::tunables().waves, cb::tunables().pdl != 0};
+    }
     int32_t cuda_fail(cudaError_t e, const char *what) const;
     int32_t drv_fail(CUresult r, const char *what) const;
     int32_t use() const;  // cudaSetDevice

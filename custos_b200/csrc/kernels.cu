@@ -127,9 +127,17 @@ struct BinOp {  // integers: wrapping, x / 0 = 0
 
 // ------------------------------------------------------------------ binary: out = lhs op rhs
 // Algorithmic traffic: 3 * sizeof(T) per element.  UNROLL tiles of 16-byte units per thread.
+// programmatic dependent launch, see cb_pdl_enter() in kernels/skeleton.cuh
+__device__ __forceinline__ void pdl_enter()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
+}
+
 template <typename T, int OP, int UNROLL>
 __global__ void __launch_bounds__(kThreads) binary_vec_kernel(const T *lhs, const T *rhs, T *out, size_t n)
 {
+    pdl_enter();
     constexpr int VEC = 16 / sizeof(T);
     const size_t nunits = n / VEC;
     const size_t tile_units = (size_t)kThreads * UNROLL;
@@ -168,6 +176,7 @@ __global__ void __launch_bounds__(kThreads) binary_vec_kernel(const T *lhs, cons
 template <typename T, int OP>
 __global__ void __launch_bounds__(kThreads) binary_scalar_kernel(const T *lhs, const T *rhs, T *out, size_t n)
 {
+    pdl_enter();
     const size_t gsz = (size_t)gridDim.x * kThreads;
     for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += gsz)
         out[i] = BinOp<T, OP>::apply(lhs[i], rhs[i]);
@@ -610,14 +619,21 @@ cudaError_t launch_binary_t(const LaunchCtx &ctx, const void *lhs, const void *r
 {
     constexpr int UNROLL = 2;
     constexpr int VEC = 16 / sizeof(T);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = ctx.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = ctx.pdl ? 1 : 0;
     if (aligned16(lhs) && aligned16(rhs) && aligned16(out)) {
-        const int grid = grid_for(n / VEC + 1, (size_t)kThreads * UNROLL, ctx.max_blocks);
-        binary_vec_kernel<T, OP, UNROLL><<<grid, kThreads, 0, ctx.stream>>>((const T *)lhs, (const T *)rhs, (T *)out, n);
-    } else {
-        const int grid = grid_for(n, (size_t)kThreads * 4, ctx.max_blocks);
-        binary_scalar_kernel<T, OP><<<grid, kThreads, 0, ctx.stream>>>((const T *)lhs, (const T *)rhs, (T *)out, n);
+        cfg.gridDim = dim3((unsigned)grid_for(n / VEC + 1, (size_t)kThreads * UNROLL, ctx.max_blocks));
+        return cudaLaunchKernelEx(&cfg, binary_vec_kernel<T, OP, UNROLL>, (const T *)lhs, (const T *)rhs, (T *)out, n);
     }
-    return cudaGetLastError();
+    cfg.gridDim = dim3((unsigned)grid_for(n, (size_t)kThreads * 4, ctx.max_blocks));
+    return cudaLaunchKernelEx(&cfg, binary_scalar_kernel<T, OP>, (const T *)lhs, (const T *)rhs, (T *)out, n);
 }
 
 template <typename T>

@@ -12,6 +12,7 @@ namespace cb {
 struct LaunchCtx {
     cudaStream_t stream;
     int max_blocks;  // persistent-grid cap: SM count x resident blocks per SM
+    bool pdl;        // launch the kernels that wait in pdl_enter() with programmatic stream serialisation
 };
 
 // fixed, hardware-independent upper bound on pass-1 blocks of the sum (8 per SM on a 148-SM B200)
