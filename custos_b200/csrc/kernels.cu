@@ -134,6 +134,24 @@ __device__ __forceinline__ void pdl_enter()
     asm volatile("griddepcontrol.launch_dependents;");
 }
 
+// launches a kernel that begins with pdl_enter() (or handles the dependency itself) with programmatic stream serialisation
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(const LaunchCtx &ctx, void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, Args... args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = ctx.pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 template <typename T, int OP, int UNROLL>
 __global__ void __launch_bounds__(kThreads) binary_vec_kernel(const T *lhs, const T *rhs, T *out, size_t n)
 {
@@ -185,6 +203,7 @@ __global__ void __launch_bounds__(kThreads) binary_scalar_kernel(const T *lhs, c
 // ------------------------------------------------------------------ fill / clear: 1 write per element
 __global__ void __launch_bounds__(kThreads) fill16_kernel(uint4 *out, size_t nunits, uint4 pattern)
 {
+    pdl_enter();
     constexpr int UNROLL = 4;
     const size_t tile_units = (size_t)kThreads * UNROLL;
     const size_t ntiles = nunits / tile_units;
@@ -201,6 +220,7 @@ __global__ void __launch_bounds__(kThreads) fill16_kernel(uint4 *out, size_t nun
 template <typename T>
 __global__ void __launch_bounds__(kThreads) fill_scalar_kernel(T *out, size_t n, T value)
 {
+    pdl_enter();
     const size_t gsz = (size_t)gridDim.x * kThreads;
     for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += gsz) out[i] = value;
 }
@@ -208,6 +228,7 @@ __global__ void __launch_bounds__(kThreads) fill_scalar_kernel(T *out, size_t n,
 // ------------------------------------------------------------------ copy: 1 read + 1 write
 __global__ void __launch_bounds__(kThreads) copy16_kernel(const uint4 *in, uint4 *out, size_t nunits)
 {
+    pdl_enter();
     constexpr int UNROLL = 4;
     const size_t tile_units = (size_t)kThreads * UNROLL;
     const size_t ntiles = nunits / tile_units;
@@ -226,6 +247,7 @@ __global__ void __launch_bounds__(kThreads) copy16_kernel(const uint4 *in, uint4
 
 __global__ void __launch_bounds__(kThreads) copy_bytes_kernel(const unsigned char *in, unsigned char *out, size_t n)
 {
+    pdl_enter();
     const size_t gsz = (size_t)gridDim.x * kThreads;
     for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += gsz) out[i] = in[i];
 }
@@ -509,7 +531,10 @@ lut16_kernel(const unsigned short *in, unsigned short *out, unsigned short *seed
              unsigned long long *counters)
 {
     extern __shared__ uint4 lut_q[];
+    // the table was written when the expression was compiled: loading it does not depend on the kernel before this one,
+    // so it happens BEFORE the dependent-launch wait and overlaps that kernel's tail
     for (int i = threadIdx.x; i < (int)(kLutBytes / 16); i += kLutThreads) lut_q[i] = table[i];
+    pdl_enter();
     __syncthreads();
     const unsigned short *lut = reinterpret_cast<const unsigned short *>(lut_q);
     const size_t nunits = n / 8;
@@ -733,19 +758,17 @@ cudaError_t launch_fill(const LaunchCtx &ctx, void *out, size_t n, int elem_byte
         const size_t cnt = nbytes / (size_t)elem_bytes;
         const int grid = grid_for(cnt, (size_t)kThreads * 4, ctx.max_blocks);
         switch (elem_bytes) {
-        case 1: fill_scalar_kernel<unsigned char><<<grid, kThreads, 0, ctx.stream>>>(p, cnt, (unsigned char)pattern); break;
-        case 2: fill_scalar_kernel<unsigned short><<<grid, kThreads, 0, ctx.stream>>>((unsigned short *)p, cnt, (unsigned short)pattern); break;
-        case 4: fill_scalar_kernel<unsigned int><<<grid, kThreads, 0, ctx.stream>>>((unsigned int *)p, cnt, (unsigned int)pattern); break;
-        default: fill_scalar_kernel<unsigned long long><<<grid, kThreads, 0, ctx.stream>>>((unsigned long long *)p, cnt, (unsigned long long)pattern); break;
+        case 1: return launch_pdl(ctx, fill_scalar_kernel<unsigned char>, grid, kThreads, 0, p, cnt, (unsigned char)pattern);
+        case 2: return launch_pdl(ctx, fill_scalar_kernel<unsigned short>, grid, kThreads, 0, (unsigned short *)p, cnt, (unsigned short)pattern);
+        case 4: return launch_pdl(ctx, fill_scalar_kernel<unsigned int>, grid, kThreads, 0, (unsigned int *)p, cnt, (unsigned int)pattern);
+        default: return launch_pdl(ctx, fill_scalar_kernel<unsigned long long>, grid, kThreads, 0, (unsigned long long *)p, cnt, (unsigned long long)pattern);
         }
-        return cudaGetLastError();
     };
     if (!aligned16(base)) return scalar(base, bytes);  // sub-slices that do not start on a 16-byte boundary
     const size_t units = bytes / 16;
     if (units) {
         const int grid = grid_for(units, (size_t)kThreads * 4, ctx.max_blocks);
-        fill16_kernel<<<grid, kThreads, 0, ctx.stream>>>((uint4 *)base, units, pat);
-        cudaError_t e = cudaGetLastError();
+        cudaError_t e = launch_pdl(ctx, fill16_kernel, grid, kThreads, 0, (uint4 *)base, units, pat);
         if (e != cudaSuccess) return e;
     }
     return scalar(base + units * 16, bytes - units * 16);
@@ -767,21 +790,18 @@ cudaError_t launch_copy(const LaunchCtx &ctx, void *dst, const void *src, size_t
         const size_t units = bytes / 16;
         if (units) {
             const int grid = grid_for(units, (size_t)kThreads * 4, ctx.max_blocks);
-            copy16_kernel<<<grid, kThreads, 0, ctx.stream>>>((const uint4 *)src, (uint4 *)dst, units);
-            cudaError_t e = cudaGetLastError();
+            cudaError_t e = launch_pdl(ctx, copy16_kernel, grid, kThreads, 0, (const uint4 *)src, (uint4 *)dst, units);
             if (e != cudaSuccess) return e;
         }
         const size_t rest = bytes - units * 16;
         if (rest) {
-            copy_bytes_kernel<<<1, kThreads, 0, ctx.stream>>>((const unsigned char *)src + units * 16,
-                                                              (unsigned char *)dst + units * 16, rest);
-            return cudaGetLastError();
+            return launch_pdl(ctx, copy_bytes_kernel, 1, kThreads, 0, (const unsigned char *)src + units * 16,
+                              (unsigned char *)dst + units * 16, rest);
         }
         return cudaSuccess;
     }
     const int grid = grid_for(bytes, (size_t)kThreads * 4, ctx.max_blocks);
-    copy_bytes_kernel<<<grid, kThreads, 0, ctx.stream>>>((const unsigned char *)src, (unsigned char *)dst, bytes);
-    return cudaGetLastError();
+    return launch_pdl(ctx, copy_bytes_kernel, grid, kThreads, 0, (const unsigned char *)src, (unsigned char *)dst, bytes);
 }
 
 int launch_copy_count(const void *dst, const void *src, size_t bytes)
@@ -850,9 +870,8 @@ static cudaError_t launch_lut16_t(const LaunchCtx &ctx, int sm_count, const void
     const size_t block_tiles = n / 8 / ((size_t)THREADS * UNROLL);
     int grid = sm_count;
     if ((size_t)grid > block_tiles + 1) grid = (int)(block_tiles + 1);
-    lut16_kernel<THREADS, UNROLL, GRAB, MODE><<<grid, THREADS, kLutBytes, ctx.stream>>>(
-        (const unsigned short *)in, (unsigned short *)out, (unsigned short *)seed, n, (const uint4 *)table, counters);
-    return cudaGetLastError();
+    return launch_pdl(ctx, lut16_kernel<THREADS, UNROLL, GRAB, MODE>, grid, THREADS, kLutBytes, (const unsigned short *)in,
+                      (unsigned short *)out, (unsigned short *)seed, n, (const uint4 *)table, counters);
 }
 
 cudaError_t launch_lut16(const LaunchCtx &ctx, int sm_count, const void *in, void *out, size_t n, const void *table,
