@@ -8,6 +8,7 @@ for tool in memcheck racecheck initcheck; do
   echo "$tool rc=$?" | tee -a gpurun_out/r2_sanitize_$tool.log
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize_kernels|launches" gpurun_out/r2_sanitize_$tool.log | tail -4
 done
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1; tail -1 gpurun_out/r2_smoke.log
 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; head -c 300 gpurun_out/bench_final.json; echo
 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_final_ref.json 2>/dev/null
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_launches_bench.csv python bench.py --steps 20 --warmup 3 > gpurun_out/r2_launches_bench.log 2>&1
