@@ -368,7 +368,9 @@ int32_t cbm_device_raw(cbm_device *d, cb_device **raw);
  * works on the slice unchanged and without communication, results inherit the slice of their parents, and
  * cbm_sum / cbm_mean of a sharded buffer return the GLOBAL value — the rank's deterministic partial, one scalar per
  * rank exchanged over NVLink, folded in rank order: identical bits on every rank.  All ranks must call cbm_sum /
- * cbm_mean of sharded buffers in the same order (they are collective). */
+ * cbm_mean of sharded buffers in the same order (they are collective).  The communicator stays owned by the caller:
+ * it must outlive the device (or be detached with cbm_device_set_comm(d, NULL) first); cbm_device_destroy does not
+ * destroy it. */
 int32_t cbm_device_set_comm(cbm_device *d, cb_comm *comm);
 int32_t cbm_buffer_new_sharded(cbm_device *d, int32_t dtype, size_t global_len, cbm_buf *out);
 /* `global_data` is the whole host array (global_len elements); only this rank's slice is read and uploaded */
