@@ -173,3 +173,44 @@ def test_sum_2p30(raw_device):
     got = dev.sum(N.F32, p, n)
     assert abs(float(got) - 64 * float(np.sum(signed.astype(np.float64)))) <= 1e-6 * 64 * float(np.sum(np.abs(signed.astype(np.float64))))
     dev.free(p)
+
+
+@pytest.mark.parametrize("dt", [N.F32, N.F16])
+def test_fused_backward_2p28(raw_device, dt):
+    # BASELINE configs[2] with Autograd at full size: the one-kernel backward of CHAIN8 (f16: the looked-up seeded form)
+    # over 2^28 elements — periodic inputs give periodic gradients (whole-buffer checksums), every tile equals the
+    # 2^24 launch, which in turn equals the eight add_unary_grad kernels of the unfused tape bit for bit
+    dev = raw_device
+    npdt = {N.F32: np.float32, N.F16: np.float16}[dt]
+    block = np.random.default_rng(4).uniform(-4, 4, BLOCK).astype(npdt)
+    isz = block.itemsize
+    x = tiled(dev, dt, block, FULL)
+    grad, seed = dev.alloc(FULL * isz), dev.alloc(FULL * isz, zero=False)
+    e = dev.compile(CHAIN8 + CHAIN8_GRADS, dt, N.KERNEL_CHAIN_GRAD)
+    dev.unary_grad_ex(e, x, grad, seed, FULL, N.GRAD_SEED_ONES)
+    # the unfused tape on one block: activations, then eight grad kernels over zeroed gradient buffers
+    pb = dev.upload(block)
+    acts = [pb]
+    for f in CHAIN8[:-1]:
+        nxt = dev.alloc(BLOCK * isz)
+        dev.apply(dev.compile(f, dt), acts[-1], nxt, BLOCK)
+        acts.append(nxt)
+    g_prev = dev.alloc(BLOCK * isz)
+    dev.fill(dt, g_prev, BLOCK, 1.0)
+    for k in reversed(range(8)):
+        g_k = dev.alloc(BLOCK * isz)  # zeroed
+        dev.unary_grad(dev.compile(CHAIN8_GRADS[k], dt, N.KERNEL_UNARY_GRAD), acts[k], g_k, g_prev, BLOCK)
+        dev.free(g_prev)
+        g_prev = g_k
+    utype, words = (N.U32, BLOCK) if dt == N.F32 else (N.U8, BLOCK * 2)
+    per_tile = dev.sum(utype, g_prev, words)
+    for t in (0, 3, 9, 15):
+        assert dev.sum(utype, grad + t * BLOCK * isz, words) == per_tile, f"tile {t}"
+    idx = sample_positions(FULL)
+    got = gather(dev, dt, grad, idx, isz)
+    small = dev.d2h(g_prev, BLOCK, dt)
+    assert_bit_exact(got, small[idx % BLOCK], "fused 2^28 backward vs the unfused tape on the block")
+    one = dev.sum(utype, seed, words * (FULL // BLOCK))  # the seed was written by the kernel: all ones
+    assert one == (FULL * 0x3f800000 if dt == N.F32 else FULL * (0x3c + 0x00)), "seed is not all ones"
+    for p in acts + [x, grad, seed, g_prev]:
+        dev.free(p)
