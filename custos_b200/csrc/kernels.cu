@@ -512,6 +512,29 @@ __device__ __forceinline__ unsigned int add16x2(unsigned int g, unsigned int t)
     else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(s1), "f"(s0));
     return r;
 }
+// o * t for two packed 16-bit lanes: the f32 product (exact for binary16 operands) rounded once to 16 bits, as `half` does
+template <bool BF16>
+__device__ __forceinline__ unsigned int mul16x2(unsigned int o, unsigned int t)
+{
+    float o0, o1, t0, t1;
+    if (BF16) {
+        o0 = __uint_as_float(o << 16), o1 = __uint_as_float(o & 0xffff0000u);
+        t0 = __uint_as_float(t << 16), t1 = __uint_as_float(t & 0xffff0000u);
+    } else {
+        o0 = h2f((unsigned short)(o & 0xffffu)), o1 = h2f((unsigned short)(o >> 16));
+        t0 = h2f((unsigned short)(t & 0xffffu)), t1 = h2f((unsigned short)(t >> 16));
+    }
+    const float p0 = __fmul_rn(o0, t0), p1 = __fmul_rn(o1, t1);
+    unsigned int r;
+    if (BF16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(p1), "f"(p0));
+    else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(p1), "f"(p0));
+    return r;
+}
+template <bool BF16>
+__device__ __forceinline__ uint4 mul16x8(uint4 o, uint4 t)
+{
+    return make_uint4(mul16x2<BF16>(o.x, t.x), mul16x2<BF16>(o.y, t.y), mul16x2<BF16>(o.z, t.z), mul16x2<BF16>(o.w, t.w));
+}
 template <bool BF16>
 __device__ __forceinline__ uint4 add16x8(uint4 g, uint4 t)
 {
@@ -525,6 +548,8 @@ __device__ __forceinline__ uint4 add16x8(uint4 g, uint4 t)
 //   function of x alone, table[x] = (((1 * gK(x_{K-1})) ...) * g1(x)) with every 16-bit rounding of the reference:
 //   grad[i] = grad[i] + table[in[i]] (one 16-bit add, through f32 like `half`) and seed[i] = 1.
 //   4 x 2 bytes per element instead of the FP32-pipe-bound chain-grad arithmetic.
+// MODE 3 / 4 (f16 / bf16): add_unary_grad of ONE op with a general out_grad — the same table holds g(lhs) (1 * g is g):
+//   grad[i] = grad[i] + seed[i] * table[in[i]], multiply then add, each rounded to 16 bits (`seed` is read here).
 template <int kLutThreads, int kLutUnroll, int kLutGrab, int MODE>
 __global__ void __launch_bounds__(kLutThreads, 1)
 lut16_kernel(const unsigned short *in, unsigned short *out, unsigned short *seed, size_t n, const uint4 *table,
@@ -546,7 +571,8 @@ lut16_kernel(const unsigned short *in, unsigned short *out, unsigned short *seed
     // the shared-memory work (the block-tile version was latency bound: LSU data pipe at 67 %, 16 long-scoreboard
     // stall cycles per issue, profiles/r2_lut16_ncu.txt).
     constexpr bool kGrad = MODE != 0;
-    constexpr bool kBf16 = MODE == 2;
+    constexpr bool kMul = MODE >= 3;  // out_grad is an input, not the seed to write
+    constexpr bool kBf16 = MODE == 2 || MODE == 4;
     constexpr unsigned int kOne = kBf16 ? 0x3f803f80u : 0x3c003c00u;
     const uint4 ones = make_uint4(kOne, kOne, kOne, kOne);
     const size_t tile_units = (size_t)32 * kLutUnroll;
@@ -559,11 +585,13 @@ lut16_kernel(const unsigned short *in, unsigned short *out, unsigned short *seed
     size_t tile = ((size_t)blockIdx.x * (kLutThreads / 32) + (threadIdx.x >> 5)) * kLutGrab;
     size_t grab_end = tile + kLutGrab;
     uint4 cur[kLutUnroll], nxt[kLutUnroll], gcur[kGrad ? kLutUnroll : 1], gnxt[kGrad ? kLutUnroll : 1];
+    uint4 ocur[kMul ? kLutUnroll : 1], onxt[kMul ? kLutUnroll : 1];
     if (tile < ntiles) {
 #pragma unroll
         for (int u = 0; u < kLutUnroll; u++) {
             cur[u] = ld16(pin + tile * tile_units + (size_t)u * 32 + lane);
             if (kGrad) gcur[u] = ld16(pout + tile * tile_units + (size_t)u * 32 + lane);
+            if (kMul) ocur[u] = ld16(pseed + tile * tile_units + (size_t)u * 32 + lane);
         }
     }
     while (tile < ntiles) {
@@ -579,12 +607,15 @@ lut16_kernel(const unsigned short *in, unsigned short *out, unsigned short *seed
             for (int u = 0; u < kLutUnroll; u++) {
                 nxt[u] = ld16(pin + next * tile_units + (size_t)u * 32 + lane);
                 if (kGrad) gnxt[u] = ld16(pout + next * tile_units + (size_t)u * 32 + lane);
+                if (kMul) onxt[u] = ld16(pseed + next * tile_units + (size_t)u * 32 + lane);
             }
         }
 #pragma unroll
         for (int u = 0; u < kLutUnroll; u++) {
             const size_t at = tile * tile_units + (size_t)u * 32 + lane;
-            if (kGrad) {
+            if (kMul) {
+                st16(pout + at, add16x8<kBf16>(gcur[u], mul16x8<kBf16>(ocur[u], lut8(lut, cur[u]))));
+            } else if (kGrad) {
                 st16(pout + at, add16x8<kBf16>(gcur[u], lut8(lut, cur[u])));
                 st16(pseed + at, ones);
             } else {
@@ -595,6 +626,7 @@ lut16_kernel(const unsigned short *in, unsigned short *out, unsigned short *seed
         for (int u = 0; u < kLutUnroll; u++) {
             cur[u] = nxt[u];
             if (kGrad) gcur[u] = gnxt[u];
+            if (kMul) ocur[u] = onxt[u];
         }
         tile = next;
     }
@@ -602,7 +634,9 @@ lut16_kernel(const unsigned short *in, unsigned short *out, unsigned short *seed
     const size_t gid = (size_t)blockIdx.x * kLutThreads + threadIdx.x;
     const size_t gsz = (size_t)gridDim.x * kLutThreads;
     for (size_t u = ntiles * tile_units + gid; u < nunits; u += gsz) {
-        if (kGrad) {
+        if (kMul) {
+            st16(pout + u, add16x8<kBf16>(ld16(pout + u), mul16x8<kBf16>(ld16(pseed + u), lut8(lut, ld16(pin + u)))));
+        } else if (kGrad) {
             st16(pout + u, add16x8<kBf16>(ld16(pout + u), lut8(lut, ld16(pin + u))));
             st16(pseed + u, ones);
         } else {
@@ -610,7 +644,9 @@ lut16_kernel(const unsigned short *in, unsigned short *out, unsigned short *seed
         }
     }
     for (size_t i = nunits * 8 + gid; i < n; i += gsz) {
-        if (kGrad) {
+        if (kMul) {
+            out[i] = (unsigned short)(add16x2<kBf16>(out[i], mul16x2<kBf16>(seed[i], lut[in[i]])) & 0xffffu);
+        } else if (kGrad) {
             out[i] = (unsigned short)(add16x2<kBf16>(out[i], lut[in[i]]) & 0xffffu);
             seed[i] = (unsigned short)(kOne & 0xffffu);
         } else {
@@ -893,6 +929,15 @@ cudaError_t launch_lut16_grad_seed(const LaunchCtx &ctx, int sm_count, int dtype
     (void)cudaGetLastError();
     if (dtype == CB_BF16) return launch_lut16_t<512, 4, 8, 2>(ctx, sm_count, x, x_grad, out_grad, n, table, counters);
     return launch_lut16_t<512, 4, 8, 1>(ctx, sm_count, x, x_grad, out_grad, n, table, counters);
+}
+
+cudaError_t launch_lut16_grad_mul(const LaunchCtx &ctx, int sm_count, int dtype, const void *x, void *x_grad, const void *out_grad,
+                                  size_t n, const void *table, unsigned long long *counters)
+{
+    (void)cudaGetLastError();
+    void *og = const_cast<void *>(out_grad);  // read only in these modes
+    if (dtype == CB_BF16) return launch_lut16_t<512, 4, 8, 4>(ctx, sm_count, x, x_grad, og, n, table, counters);
+    return launch_lut16_t<512, 4, 8, 3>(ctx, sm_count, x, x_grad, og, n, table, counters);
 }
 
 cudaError_t launch_fold_ranks(const LaunchCtx &ctx, int dtype, const void *gathered, int n_ranks, void *out, size_t divisor)

@@ -57,6 +57,9 @@ cudaError_t launch_lut16(const LaunchCtx &ctx, int sm_count, const void *in, voi
 // seeded backward of a 16-bit chain: x_grad[i] += table[x[i]], out_grad[i] = 1 (dtype CB_F16 or CB_BF16)
 cudaError_t launch_lut16_grad_seed(const LaunchCtx &ctx, int sm_count, int dtype, const void *x, void *x_grad, void *out_grad,
                                    size_t n, const void *table, unsigned long long *counters);
+// add_unary_grad of one 16-bit op with a general out_grad: x_grad[i] += out_grad[i] * table[x[i]] (table = g(x))
+cudaError_t launch_lut16_grad_mul(const LaunchCtx &ctx, int sm_count, int dtype, const void *x, void *x_grad, const void *out_grad,
+                                  size_t n, const void *table, unsigned long long *counters);
 cudaError_t launch_fold_ranks(const LaunchCtx &ctx, int dtype, const void *gathered, int n_ranks, void *out, size_t divisor);
 
 }  // namespace cb

@@ -362,10 +362,26 @@ def test_seeded_16bit_backward_by_lookup_matches_the_arithmetic_kernel(raw_devic
     want_g, want_o = dev.d2h(pg, n, N.U16), dev.d2h(po, n, N.U16)
     assert np.all(want_o == one) and np.all(got_o == one)
     assert got_g.tobytes() == want_g.tobytes(), f"{int(np.sum(got_g != want_g))} of {n} gradients differ"
-    # unseeded calls never take the table
+    # unseeded with out_grad = 1 gives the same gradient (a chain keeps the arithmetic kernel, one op looks g(lhs) up)
     dev.h2d(pg, g0)
     dev.fill(dt, po, n, 1.0)
     dev.unary_grad_ex(e, px, pg, po, n, 0)
     assert dev.d2h(pg, n, N.U16).tobytes() == want_g.tobytes()
+    # a general out_grad: for ONE op the table holds g(lhs) and the kernel multiplies and adds in 16 bits
+    og = rng.integers(0, 65536, n).astype(np.uint16)
+    og[:8] = [0x0000, 0x8000, one, one | 0x8000, 0x7c00 if dt == N.F16 else 0x7f80, 0x0001, 0x7e00 if dt == N.F16 else 0x7fc0, 0x3800]
+    results = []
+    for use_lut in (True, False):
+        dev.h2d(pg, g0)
+        dev.h2d(po, og)
+        dev.set_lut(e, use_lut)
+        before = dev.launches
+        dev.unary_grad(e, px, pg, po, n)
+        assert dev.launches - before == 1
+        results.append(dev.d2h(pg, n, N.U16))
+    dev.set_lut(e, True)
+    nan = (lambda b: ((b & 0x7c00) == 0x7c00) & ((b & 0x3ff) != 0)) if dt == N.F16 else bf16_is_nan
+    same = (results[0] == results[1]) | (nan(results[0]) & nan(results[1]))
+    assert np.all(same), f"{int(np.sum(~same))} of {n} gradients differ with a general out_grad ({kind})"
     for p in (px, pg, po):
         dev.free(p)
