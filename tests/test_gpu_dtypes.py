@@ -376,7 +376,7 @@ def test_seeded_16bit_backward_by_lookup_matches_the_arithmetic_kernel(raw_devic
         dev.h2d(po, og)
         dev.set_lut(e, use_lut)
         before = dev.launches
-        dev.unary_grad(e, px, pg, po, n)
+        dev.unary_grad_ex(e, px, pg, po, n, 0)
         assert dev.launches - before == 1
         results.append(dev.d2h(pg, n, N.U16))
     dev.set_lut(e, True)
