@@ -232,7 +232,8 @@ int32_t cb_expr_release(cb_expr *e);   /* expressions are owned by the device ca
  * arithmetic kernel at compile time); cb_apply of >= CB_LUT16_MIN_ELEMS (2^22) 16-byte-aligned elements runs as a
  * shared-memory table lookup — same bits, HBM-bound instead of FP32-pipe-bound.  f16 / bf16 UNARY_GRAD and
  * CHAIN_GRAD expressions carry the table of their backward term for out_grad = 1: cb_unary_grad_ex with
- * CB_GRAD_SEED_ONES on a large buffer is then one lookup and one 16-bit add per element.  Off per expression with
+ * CB_GRAD_SEED_ONES on a large buffer is then one lookup and one 16-bit add per element (a single-op UNARY_GRAD
+ * also with a general out_grad: lookup of g(lhs), 16-bit multiply and add).  Off per expression with
  * cb_expr_set_lookup(e, 0), off for the process with CB_LUT16=0. */
 int32_t cb_expr_set_lookup(cb_expr *e, int32_t enabled);
 int32_t cb_expr_has_lookup(cb_expr *e, int32_t *flag);
