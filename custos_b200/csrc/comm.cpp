@@ -68,7 +68,7 @@ struct cb_comm {
     int n_ranks = 1, rank = 0;
     void *local = nullptr;     // this rank's partial (8 bytes)
     void *gathered = nullptr;  // n_ranks partials
-    // peer-memory exchange (fused pass 2 + exchange kernel); NCCL is only used to set it up
+    // peer-memory exchange (the last block of the sum kernel folds and exchanges); NCCL is only used to set it up
     bool p2p = false;
     cb::XchgSlot *xchg = nullptr;                 // this rank's buffer: 2 parities x n_ranks slots
     std::vector<void *> opened;                   // peers' buffers mapped through CUDA IPC

@@ -271,8 +271,9 @@ int32_t cb_binary(cb_device *dev, int32_t dtype, int32_t op, uint64_t lhs, uint6
                   uint64_t out, size_t n);
 
 /* ------------------------------------------------------------- reductions */
-/* Deterministic two-pass sum (no atomics, fixed grid): pass 1 = per-block tree over
- * a contiguous chunk, pass 2 = one block folds the partials in index order.
+/* Deterministic sum in a fixed two-level order (no atomics on data, fixed grid): level 1 = per-block tree
+ * over a contiguous chunk, level 2 = the partials folded in index order — both in ONE launch: the block that
+ * finishes last folds (which block that is does not matter to the result).
  * The result is written to a device scalar of the accumulation type
  * (f32 -> f32, f64 -> f64, f16 -> f32, integers -> i64) at `out`.
  * The reference has no sum; the order is defined in DESIGN.md. */
@@ -325,7 +326,7 @@ int32_t cb_comm_destroy(cb_comm *c);
 /* 1 when the totals are exchanged by the fused reduce+exchange kernel over NVLink peer memory (CUDA IPC),
  * 0 when the communicator fell back to ncclAllGather + fold (CB_COMM_P2P=0 forces the fallback) */
 int32_t cb_comm_uses_peer_memory(cb_comm *c, int32_t *flag);
-/* local two-pass sum of `in`, then exchange + rank-ordered fold; out = device scalar */
+/* local deterministic sum of `in`, then exchange + rank-ordered fold, all in one kernel; out = device scalar */
 int32_t cb_comm_sum(cb_comm *c, int32_t dtype, uint64_t in, size_t n_local, uint64_t out);
 int32_t cb_comm_mean(cb_comm *c, int32_t dtype, uint64_t in, size_t n_local, size_t n_global,
                      uint64_t out);
