@@ -114,3 +114,41 @@ def test_random_two_marker_expressions_and_grads(raw_device, dt, rnd):
         assert_same(dt, dev.d2h(pg, x.size, dt), orc.add_unary_grad(t, dt, x, g0, y), f"grad dtype {dt}: {to_cl_source(t, dt)}")
     for p in (px, py, po, pg):
         dev.free(p)
+
+
+@pytest.mark.parametrize("rnd", range(ROUNDS))
+@pytest.mark.parametrize("dt", ALL_NUMBERS)
+def test_random_chain_grads_equal_the_replayed_tape(raw_device, dt, rnd):
+    """CB_KERNEL_CHAIN_GRAD on random chains of exactly-rounded closures, every dtype: the one recomputing kernel
+    against the oracle's restatement of what the tape does — activations op by op, then K `add_unary_grad` calls in
+    reverse over zero-initialised intermediate gradients (src/unary.rs:118-128, src/modules/autograd/tape.rs:39-47).
+    Seeded (the kernel writes the ones) and with a general out_grad; bit-exact."""
+    dev = raw_device
+    rng = random.Random(3000 + dt + 7919 * rnd)
+    bins, uns, lits = ops_for(dt)
+    x, og, g0 = inputs_for(dt, 2053, 90 + dt), inputs_for(dt, 2053, 91 + dt), inputs_for(dt, 2053, 92 + dt)
+    px, pog, pg = dev.upload(x), dev.upload(og), dev.upload(g0)
+    one = np.ones(1, NP[dt])[0] if dt != N.BF16 else np.uint16(0x3f80)
+    for _ in range(6):
+        K = rng.randint(1, 5)
+        fwd = [rand_tree(rng, rng.randint(0, 2), [Resolve("x")], bins, uns, lits) for _ in range(K)]
+        grads = [rand_tree(rng, rng.randint(0, 2), [Resolve("x")], bins, uns, lits) for _ in range(K)]
+        e = dev.compile(fwd + grads, dt, N.KERNEL_CHAIN_GRAD)
+        acts = [x]
+        for f in fwd[:-1]:
+            acts.append(orc.apply_fn(f, dt, acts[-1]))
+        what = " ; ".join(to_cl_source(t, dt) for t in fwd) + " | " + " ; ".join(to_cl_source(t, dt) for t in grads)
+        for seeded in (False, True):
+            seed = np.full(x.size, one, NP[dt]) if seeded else og
+            want = seed
+            for k in reversed(range(K)):
+                into = g0 if k == 0 else np.zeros_like(x)
+                want = orc.add_unary_grad(grads[k], dt, acts[k], into, want)
+            dev.h2d(pg, g0)
+            dev.h2d(pog, og)
+            dev.unary_grad_ex(e, px, pg, pog, x.size, N.GRAD_SEED_ONES if seeded else 0)
+            assert_same(dt, dev.d2h(pg, x.size, dt), want, f"chain grad dtype {dt} seeded={seeded}: {what}")
+            if seeded:
+                assert np.all(dev.d2h(pog, x.size, dt) == one), "the kernel did not write the seed"
+    for p in (px, pog, pg):
+        dev.free(p)
