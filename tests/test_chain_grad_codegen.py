@@ -142,3 +142,47 @@ def test_seeded_backward_of_chain8_matches_the_golden_gradient():
     term = interpret_pair_function(pair_body(src), x, np.ones_like(x))
     assert np.all(term == np.float32(-1.0))
     assert g["chain8_grad_f32"].shape == x.shape
+
+
+@pytest.mark.parametrize("dt", [N.F16, N.BF16])
+def test_generated_16bit_backward_word_function_equals_the_replayed_tape(dt, cases=150):
+    """The f16 / bf16 chain-grad kernel runs the joined backward expression two lanes per 32-bit word (`cb_fnw`): the
+    emitted text interpreted with NumPy (every op: widen to f32, one IEEE operation, round to 16 bits) against the
+    oracle's op-by-op replay, bit for bit — the same check the f32 pair function gets above."""
+    from custos_b200.expr import bf16_from_f32  # noqa: F401
+    from tests.test_half_codegen import Half, interpret_word_function, same_bits
+    h = Half(dt)
+    rng = random.Random(40 + dt)
+    lits = [0.5, 2.0, -1.5, 3.0, 0.25, 1.0, -0.0, 8.0, -0.75, 0.0, -1.0, 100.0, 6.1035e-05]
+    data = np.random.default_rng(40 + dt)
+    etype = np.float16 if dt == N.F16 else np.float32
+    x = h.narrow(np.concatenate([data.uniform(-4, 4, 300).astype(np.float32), edge_values(etype).astype(np.float32)]))
+    og = h.narrow(np.concatenate([data.uniform(-2, 2, x.size - 6).astype(np.float32), np.array([0.0, -0.0, 1.0, -1.0, np.inf, 6e-8], np.float32)]))
+    x_grad = data.permutation(h.narrow(np.concatenate([data.uniform(-1, 1, x.size - 4).astype(np.float32), np.array([0.0, -0.0, -0.0, 0.0], np.float32)])))
+    as_dt = (lambda b: b.view(np.float16)) if dt == N.F16 else (lambda b: b)
+
+    def tree(depth):
+        roll = rng.random()
+        if depth == 0 or roll < 0.2:
+            return Resolve("x") if rng.random() < 0.6 else Combiner._wrap(rng.choice(lits))
+        if roll < 0.35:
+            return getattr(tree(depth - 1), rng.choice(["neg", "abs", "identity"]))()
+        return getattr(tree(depth - 1), rng.choice(["add", "mul", "sub", "add", "mul", "min", "max", "geq"]))(tree(depth - 1))
+    for case in range(cases):
+        K = rng.randint(1, 5)
+        fwd = [tree(rng.randint(0, 2)) for _ in range(K)]
+        grads = [tree(rng.randint(0, 2)) for _ in range(K)]
+        acts = [as_dt(x)]
+        for f in fwd[:-1]:
+            acts.append(orc.apply_fn(f, dt, acts[-1]))
+        want = as_dt(og)
+        for k in reversed(range(K)):
+            into = as_dt(x_grad) if k == 0 else np.zeros_like(as_dt(x))
+            want = orc.add_unary_grad(grads[k], dt, acts[k], into, want)
+        src = chain_grad_source(fwd, grads, dt)
+        start = src.index("cb_fnw(cb_w x, cb_w y, bool &redo)")
+        body = src[start:src.index("#endif", start)]
+        term = interpret_word_function(body, h, x, og)
+        with np.errstate(all="ignore"):
+            got = h.narrow(h.widen(x_grad) + h.widen(term))
+        assert same_bits(h, got, np.asarray(want).view(np.uint16)), f"dtype {dt} case {case} (K={K}):\n{body}"
