@@ -1248,6 +1248,11 @@ extern "C" int32_t cbm_unary_fusing(cbm_device *d)
             op_idx.push_back(oi);
         }
         size_t i = 0;
+        auto on_tape = [&](const Op &o) {
+            for (const GradOp &g : d->tape)
+                if (!g.chain && g.buf_id == o.arg_ids[1] && g.out_id == o.arg_ids[0]) return true;
+            return false;
+        };
         while (i < op_idx.size()) {
             auto fusable = [&](size_t k, int32_t dtype, size_t prev_k) {
                 if (op_idx[k] < 0) return false;
@@ -1258,7 +1263,11 @@ extern "C" int32_t cbm_unary_fusing(cbm_device *d)
                 // with a caller-owned output (cbm_binary_into, a recorded add_unary_grad) reads buffers the graph knows
                 // nothing about, and fusing the producer away would feed it zeros
                 const uint64_t mid = d->ops[(size_t)op_idx[prev_k]].arg_ids[0];
-                return o.arg_ids[1] == mid && readers_of(d, mid) == 1;
+                if (o.arg_ids[1] != mid || readers_of(d, mid) != 1) return false;
+                // a run is made of ops that all have a grad function on the tape (unary_ew) or that all have none
+                // (apply_fn): a mixed chain is split where that changes, so each part can be fused — the recorded part
+                // together with its grad functions — instead of the whole chain staying unfused
+                return on_tape(o) == on_tape(d->ops[(size_t)op_idx[prev_k]]);
             };
             if (op_idx[i] < 0 || !(d->ops[(size_t)op_idx[i]].kind == OpKind::Apply && d->ops[(size_t)op_idx[i]].unary_hint)) {
                 i++;

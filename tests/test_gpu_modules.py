@@ -832,3 +832,43 @@ def test_fusing_and_aliasing_respect_readers_the_graph_does_not_know():
             a1 = orc.apply_fn(lambda v: v.mul(2.0), orc.F32, x)
             assert_bit_exact(side.read(), orc.binary(0, orc.F32, a1, x), "the caller-owned binary op saw the real x1")
             assert_bit_exact(x3.replace().read(), orc.apply_chain([lambda v: v.mul(2.0), lambda v: v.add(1.0), lambda v: v.neg()], orc.F32, x), "chain")
+
+
+def test_a_mixed_chain_is_split_where_the_tape_starts_and_both_parts_fuse():
+    # apply_fn, apply_fn | unary_ew x 3 | apply_fn, apply_fn: three runs -> three forward kernels, and the three grad
+    # functions of the middle part become one chain-grad kernel; x2 (the input of the recorded part) stays materialised
+    n = 20_011
+    x = random_inputs(N.F32, n, 23, -2, 2)
+    fns = [lambda v: v.mul(0.5), lambda v: v.add(0.25)]
+    ews = [(lambda v: v.sin(), lambda v: v.cos()), (lambda v: v.mul(v), lambda v: v.mul(2.0)), (lambda v: v.tanh(), lambda v: v.tanh().mul(v.tanh()).neg().add(1.0))]
+    tail = [lambda v: v.neg(), lambda v: v.add(1.0)]
+
+    def program(dev):
+        buf = dev.buffer(x)
+        cur = buf
+        for f in fns:
+            cur = dev.apply_fn(cur, f)
+        mid_in = cur.require_grad()
+        for f, g in ews:
+            cur = dev.unary_ew(cur, f, g)
+        mid_out = cur
+        for f in tail:
+            cur = dev.apply_fn(cur, f)
+        return mid_in, mid_out, cur
+    with CUDA("Autograd", "Base") as dev:  # eager reference
+        mid_in, mid_out, out = program(dev)
+        mid_out.backward()
+        want = (out.read(), mid_in.grad().read())
+    with CUDA("Lazy", "Graph", "Autograd", "Base") as dev:
+        mid_in, mid_out, out = program(dev)
+        dev.unary_fusing()
+        dev.run()
+        before = dev.raw.launches
+        dev.run()
+        assert dev.raw.launches - before == 3, "three homogeneous runs, three kernels"
+        mid_out.backward()  # (the first backward also creates and zero-fills the gradient buffers)
+        assert_bit_exact(out.replace().read(), want[0], "forward")
+        assert_bit_exact(mid_in.grad().read(), want[1], "gradient of the recorded part")
+        before = dev.raw.launches
+        mid_out.backward()
+        assert dev.raw.launches - before == 1, "the three grad functions of the recorded part are one chain-grad kernel"
